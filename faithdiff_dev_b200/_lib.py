@@ -1,0 +1,72 @@
+"""ctypes binding of libfaithdiff_b200.so (the C-ABI in include/faithdiff_b200.h).
+
+There is NO fallback: if the shared library is missing the import raises, and every op raises RuntimeError
+with fd_last_error() on a non-zero status.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfaithdiff_b200.so")
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p * 2), ("a_cols", C.c_int64 * 2), ("a_ld", C.c_int64 * 2), ("b", C.c_void_p),
+        ("M", C.c_int64), ("N", C.c_int64), ("mode", C.c_int32), ("batch", C.c_int32), ("in_h", C.c_int32),
+        ("in_w", C.c_int32), ("pad_lo", C.c_int32), ("act", C.c_int32), ("bias_along_m", C.c_int32),
+        ("out_fp32", C.c_int32), ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rows_per_batch", C.c_int64),
+        ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("alpha", C.c_float), ("block_n", C.c_int32),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "faithdiff_dev_b200: %s not found — build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the CUDA path)" % LIB_PATH)
+    return C.CDLL(LIB_PATH)
+
+
+lib = _load()
+lib.fd_last_error.restype = C.c_char_p
+lib.fd_launch_count.restype = C.c_int64
+lib.fd_groupnorm_work_floats.restype = C.c_int64
+lib.fd_colorfix_work_floats.restype = C.c_int64
+
+i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
+_SIGS = {
+    "fd_gemm": [C.POINTER(GemmDesc), vp],
+    "fd_attention_d64": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
+    "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
+    "fd_groupnorm_work_floats": [i32, i32],
+    "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
+    "fd_layernorm": [vp, vp, vp, vp, i64, i32, f32, vp],
+    "fd_upsample2x_nhwc": [vp, vp, i32, i32, i32, i32, vp],
+    "fd_nchw_to_nhwc": [vp, i32, vp, i32, i32, i64, vp],
+    "fd_nhwc_to_nchw": [vp, vp, i32, i32, i32, i64, vp],
+    "fd_conv3x3_small": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "fd_linear_smallm": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "fd_timestep_embedding": [vp, vp, i32, i32, i64, vp],
+    "fd_batch_axis_attention": [vp, vp, i32, i64, i32, i32, vp],
+    "fd_tile_gather": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
+    "fd_tile_blend": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
+    "fd_cfg_euler_blend": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp],
+    "fd_tile_accumulate": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
+    "fd_seam_blend": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
+    "fd_image_preprocess": [vp, vp, vp, i32, i32, vp],
+    "fd_image_postprocess": [vp, i32, vp, i32, i32, vp],
+    "fd_colorfix_work_floats": [i32, i32],
+    "fd_adain_color_fix": [vp, vp, vp, i32, i32, vp, vp],
+    "fd_wavelet_color_fix": [vp, vp, vp, i32, i32, vp, vp],
+}
+EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count"] + list(_SIGS)
+for _n, _a in _SIGS.items():
+    getattr(lib, _n).argtypes = _a
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, status, lib.fd_last_error().decode()))

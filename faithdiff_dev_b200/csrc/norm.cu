@@ -1,0 +1,228 @@
+// HBM-bound normalisation kernels on NHWC bf16 activations.
+//   GroupNorm(+SiLU): (1) partial sums per (sample, pixel-chunk, group) — 16-byte vector loads, per-thread fixed
+//   channel lanes, shared-memory combine, deterministic (no atomics); (2) finalize → per-(sample, channel)
+//   scale/shift tables; (3) streaming apply y = silu(x*scale + shift).  The second read of x hits L2 for the
+//   UNet's tensors (<= 42 MB vs 126 MB L2), so DRAM traffic is ~ one read + one write.
+//   Two NHWC sources are treated as one channel-concatenated tensor (the up-block torch.cat never materialises).
+//   LayerNorm: one warp per row, row held in registers, warp-shuffle reductions.
+#include "common.cuh"
+#include "../../include/faithdiff_b200.h"
+
+namespace fd {
+extern int64_t g_launches;
+constexpr int kGnMaxChunks = 296;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// grid (nchunks, B); block V*R threads, V = Ct/8 channel vectors, R pixel rows in flight
+__global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
+                                  int c1, long long hw, int groups, int R, float* __restrict__ partial) {
+  extern __shared__ float sm[];
+  const int ct = c0 + c1, V = ct >> 3;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const long long per = (hw + nchunks - 1) / nchunks;
+  const long long p0 = chunk * per, p1 = (p0 + per < hw) ? p0 + per : hw;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+  const int ch = v * 8;
+  const bool from0 = ch < c0;
+  const __nv_bfloat16* base = from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0);
+  const int pitch = from0 ? c0 : c1;
+  if (r < R) {
+    for (long long p = p0 + r; p < p1; p += R) {
+      float f[8];
+      load8(base + p * pitch, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+    float* ss = sm + (size_t)r * ct + ch;
+    float* sq = sm + (size_t)(R + r) * ct + ch;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ss[j] = s[j]; sq[j] = q[j]; }
+  }
+  __syncthreads();
+  const int cpg = ct / groups;
+  for (int t = threadIdx.x; t < 2 * groups; t += blockDim.x) {
+    const int g = t >> 1, which = t & 1;
+    float acc = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      const float* row = sm + (size_t)(which * R + rr) * ct + g * cpg;
+      for (int c = 0; c < cpg; ++c) acc += row[c];
+    }
+    partial[(((long long)b * nchunks + chunk) * groups + g) * 2 + which] = acc;
+  }
+}
+
+// grid B; block 256
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int groups, int ct, long long hw,
+                                   float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.x;
+  const int cpg = ct / groups;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+      const float* pp = partial + (((long long)b * nchunks + c) * groups + g) * 2;
+      s += (double)pp[0];
+      q += (double)pp[1];
+    }
+    const double n = (double)hw * cpg;
+    const double mean = s / n;
+    double var = q / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[g] = (float)mean;
+    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < ct; c += blockDim.x) {
+    const int g = c / cpg;
+    const float sc = s_rstd[g] * gamma[c];
+    scale[(long long)b * ct + c] = sc;
+    shift[(long long)b * ct + c] = beta[c] - s_mean[g] * sc;
+  }
+}
+
+__global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1,
+                                long long hw, long long total_vec, const float* __restrict__ scale,
+                                const float* __restrict__ shift, int silu, __nv_bfloat16* __restrict__ out) {
+  const int ct = c0 + c1, V = ct >> 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % V);
+    const long long bp = i / V;
+    const int b = (int)(bp / hw);
+    const int ch = v * 8;
+    const __nv_bfloat16* src = ch < c0 ? x0 + bp * c0 + ch : x1 + bp * c1 + (ch - c0);
+    float f[8];
+    load8(src, f);
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * ct + ch));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * ct + ch + 4));
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + (long long)b * ct + ch));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + (long long)b * ct + ch + 4));
+    f[0] = f[0] * a0.x + s0.x; f[1] = f[1] * a0.y + s0.y; f[2] = f[2] * a0.z + s0.z; f[3] = f[3] * a0.w + s0.w;
+    f[4] = f[4] * a1.x + s1.x; f[5] = f[5] * a1.y + s1.y; f[6] = f[6] * a1.z + s1.z; f[7] = f[7] * a1.w + s1.w;
+    if (silu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+    }
+    store8(out + bp * ct + ch, f);
+  }
+}
+
+// one warp per row; cols <= 1280 (5 vectors of 8 per lane)
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long rows, int cols,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  const int V = cols >> 3;
+  float f[5][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      load8(x + row * cols + v * 8, f[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[i][j];
+    }
+  }
+  const float mean = warp_sum(s) / cols;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / cols + eps);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = lane + 32 * i;
+    if (v < V) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      float o[8];
+      o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
+      o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
+      o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
+      o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
+      store8(out + row * cols + v * 8, o);
+    }
+  }
+}
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups, int32_t channels) {
+  return (int64_t)batch * kGnMaxChunks * groups * 2 + (int64_t)batch * channels * 2 + 16;
+}
+
+extern "C" int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma,
+                                 const float* beta, void* out, int32_t batch, int64_t hw, int32_t groups, float eps,
+                                 int32_t silu, float* work, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x1) c1 = 0;
+  const int ct = c0 + c1;
+  FD_REQUIRE(x0 && out && work && gamma && beta, "fd_groupnorm_nhwc: null pointer");
+  FD_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0 && ct % groups == 0 && groups <= 64, "fd_groupnorm_nhwc: channels %d+%d groups %d unsupported", c0, c1, groups);
+  const int V = ct / 8;
+  FD_REQUIRE(V <= 1024, "fd_groupnorm_nhwc: too many channels");
+  int R = 512 / V;
+  if (R < 1) R = 1;
+  int nchunks = (2 * num_sms() + batch - 1) / batch;
+  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
+  if (nchunks > hw) nchunks = (int)hw;
+  if (nchunks < 1) nchunks = 1;
+  float* partial = work;
+  float* scale = work + (int64_t)batch * kGnMaxChunks * groups * 2;
+  float* shift = scale + (int64_t)batch * ct;
+  const size_t smem = (size_t)2 * R * ct * sizeof(float);
+  FD_REQUIRE(smem <= 48 * 1024, "fd_groupnorm_nhwc: smem %zu too large", smem);
+  gn_partial_kernel<<<dim3(nchunks, batch), V * R, smem, stream>>>((const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1,
+                                                                    c1, hw, groups, R, partial);
+  gn_finalize_kernel<<<batch, 256, 0, stream>>>(partial, nchunks, groups, ct, hw, eps, gamma, beta, scale, shift);
+  const long long total_vec = (long long)batch * hw * V;
+  long long blocks = (total_vec + 255) / 256;
+  const long long cap = (long long)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gn_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, hw,
+                                                       total_vec, scale, shift, silu, (__nv_bfloat16*)out);
+  g_launches += 3;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int32_t cols,
+                            float eps, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(x && out && gamma && beta, "fd_layernorm: null pointer");
+  FD_REQUIRE(cols % 8 == 0 && cols <= 1280, "fd_layernorm: cols %d unsupported (need %%8==0 and <= 1280)", cols);
+  const int threads = 256;
+  const long long blocks = (rows * 32 + threads - 1) / threads;
+  layernorm_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)out, rows,
+                                                             cols, eps);
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

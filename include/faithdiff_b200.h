@@ -1,0 +1,158 @@
+/* faithdiff_b200.h — C-ABI of libfaithdiff_b200.so (hand-written sm_100a kernels for FaithDiff's tiled
+ * latent-denoising hot path).  Plain pointers + sizes, no torch types.  All pointers are DEVICE pointers unless
+ * a name ends in _host.  Every entry point returns 0 on success; non-zero → fd_last_error() describes it.
+ * `stream` is a cudaStream_t passed as void*.  Nothing allocates device memory; work buffers are passed in.
+ *
+ * The reference (tpetkovich/FaithDiff-dev) is pure Python over diffusers/PyTorch library kernels — it has no
+ * FFI.  Each entry point therefore cites the reference *Python call site(s)* whose GPU work it replaces
+ * (paths relative to the reference root); INTEGRATION.md shows the ctypes binding and where the reference's
+ * modules would call it.
+ */
+#ifndef FAITHDIFF_B200_H
+#define FAITHDIFF_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* fd_last_error(void);
+int fd_version(void);
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches counter) */
+int64_t fd_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tensor-core implicit GEMM (tcgen05.mma, TMEM accumulators, TMA operand staging, persistent, warp-specialised)
+ *   out[M, N] = epilogue( alpha * A[M, K] · B[N, K]^T )
+ * mode 0  A = up to two row-major bf16 matrices concatenated along K           (Linear layers, 1x1 convs)
+ * mode 1  A = implicit im2col of up to two NHWC bf16 images concatenated along C, 3x3 stride 1  (conv3x3)
+ * mode 2  A = implicit im2col of one NHWC bf16 image, 3x3 stride 2             (Downsample2D)
+ * B = weights bf16 [N, taps*(C0+C1)] (tap-major, channel-minor; K contiguous).
+ * Replaces: diffusers Conv2d/Linear reached from FaithDiff/models/unet_2d_condition_vae_extension.py:571-579,
+ * :611-690 (conv_in…conv_out, ResnetBlock2D, Transformer2DModel projections, GEGLU feed-forward,
+ * ControlNetConditioningEmbedding :213-219, ResidualAttentionBlock :238-260) and the Encoder / AutoencoderKL
+ * conv stacks (:122-148; pipeline_FaithDiff_tlc.py:1272,1438).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct fd_gemm_desc {
+  const void* a[2];      /* A sources (bf16); a[1] NULL if single source                                  */
+  int64_t a_cols[2];     /* K columns (mode 0) / channels (mode 1,2) taken from each source               */
+  int64_t a_ld[2];       /* row pitch (mode 0) / pixel pitch (mode 1,2) in elements                       */
+  const void* b;         /* weights bf16 [N, K_total]                                                     */
+  int64_t M, N;          /* mode 0: rows; mode 1,2: M is derived (batch*out_h*out_w), N = out channels    */
+  int32_t mode;
+  int32_t batch, in_h, in_w; /* conv input geometry                                                       */
+  int32_t pad_lo;        /* zero padding at top/left (1: pad=1; 0: the VAE's F.pad(0,1,0,1) + pad 0)      */
+  int32_t act;           /* 0 none, 1 SiLU, 2 GEGLU (B rows interleaved h0,g0,h1,g1… → N/2 outputs), 3 QuickGELU */
+  int32_t bias_along_m;  /* bias indexed by output row instead of column                                  */
+  int32_t out_fp32;      /* out dtype: 0 bf16, 1 fp32                                                     */
+  const float* bias;     /* [N] (or [M]) fp32, or NULL                                                    */
+  const float* rowbias;  /* [M / rows_per_batch, N] fp32 added per sample (timestep embedding), or NULL   */
+  int64_t rows_per_batch;
+  const void* residual;  /* bf16 [M, ld_res] added after the activation, or NULL                          */
+  int64_t ld_res;
+  void* out;             /* [M, ld_out]                                                                   */
+  int64_t ld_out;
+  float alpha;
+  int32_t block_n;       /* 0 = auto; else multiple of 32 in [32, 256]                                    */
+} fd_gemm_desc;
+int fd_gemm(const fd_gemm_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Flash-style attention, head_dim 64, bf16, non-causal, no mask (tcgen05 QK^T and PV, online softmax in fp32).
+ *   q: rows [batch*lq], k/v: rows [batch*lk]; head h occupies columns [h*64, h*64+64) from q/k/v + pitch ld*.
+ * Replaces: F.scaled_dot_product_attention inside diffusers AttnProcessor2_0 for attn1 (self) and attn2
+ * (cross, lk = 77) of every BasicTransformerBlock reached from unet_2d_condition_vae_extension.py:617-684.
+ * --------------------------------------------------------------------------------------------------------- */
+int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                     int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream);
+
+/* row softmax: p[r, :] = softmax(alpha * s[r, :]) ; s fp32 [rows, ld_s], p bf16 [rows, ld_p]
+ * (single-head d=512 attention of the VAE / LQ-encoder mid block, unet_…extension.py:96-106)              */
+int fd_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int64_t rows, int64_t cols, float alpha,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Bandwidth-bound kernels (NHWC bf16 activations)
+ * --------------------------------------------------------------------------------------------------------- */
+/* GroupNorm(+SiLU) over the channel-concatenation of up to two NHWC sources → one NHWC output [B,HW,C0+C1].
+ * work: fp32 scratch of fd_groupnorm_work_floats(batch, groups) elements.
+ * Replaces: ResnetBlock2D.norm1/norm2 + SiLU, Transformer2DModel.norm, conv_norm_out (…extension.py:688-689),
+ * ControlNetConditioningEmbedding.norm_in (:215), torch.cat of skip connections in the up blocks.          */
+int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups);
+int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
+                      void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
+                      void* stream);
+/* LayerNorm over the last dim (affine), bf16 in/out. Replaces BasicTransformerBlock.norm1/2/3 and the
+ * FaithDiff LayerNorm (…extension.py:229-235).                                                             */
+int fd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int32_t cols, float eps,
+                 void* stream);
+/* nearest 2x upsample NHWC (Upsample2D before its conv) */
+int fd_upsample2x_nhwc(const void* x, void* out, int32_t batch, int32_t h, int32_t w, int32_t c, void* stream);
+/* NCHW <-> NHWC layout changes at the module boundary (the reference's forward signatures are NCHW). in_dtype /
+ * out_dtype: 0 bf16, 1 fp16, 2 fp32.                                                                       */
+int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out_bf16, int32_t batch, int32_t c, int64_t hw, void* stream);
+int fd_nhwc_to_nchw(const void* x_bf16, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream);
+/* direct 3x3 convs with a tiny channel count on one side (conv_in 4→C, conv_out C→4, VAE 3→128 / 128→3):
+ * x NHWC bf16 [B,H,W,cin], w bf16 [cout, 9*cin] (tap-major), out NHWC bf16.                                 */
+int fd_conv3x3_small(const void* x, const void* w, const float* bias, void* out, int32_t batch, int32_t h, int32_t wd,
+                     int32_t cin, int32_t cout, void* stream);
+/* tiny-M linear: out[m, n] = act(sum_k x[m,k] w[n,k] + bias[n]); x fp32 [M,K], w bf16 [N,K], out fp32; act 0/1(SiLU)
+ * (time / micro-conditioning embedding MLPs and the 17 time_emb_proj, …extension.py:543-564)               */
+int fd_linear_smallm(const float* x, const void* w, const float* bias, float* out, int32_t m, int32_t n, int32_t k,
+                     int32_t act_in_silu, int32_t act_out_silu, void* stream);
+/* sinusoidal timestep embedding (flip_sin_to_cos=True, shift 0): out[i, :] = [cos(v_i f), sin(v_i f)], fp32   */
+int fd_timestep_embedding(const float* values, float* out, int32_t n, int32_t dim, int64_t out_ld, void* stream);
+/* FaithDiff information-transformer attention across the BATCH axis (nn.MultiheadAttention with
+ * batch_first=False fed (B, HW, E), …extension.py:242,576-577): qkv bf16 [B, HW, 3E] → out bf16 [B, HW, E]   */
+int fd_batch_axis_attention(const void* qkv, void* out, int32_t batch, int64_t hw, int32_t embed, int32_t heads,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Tiled-latent kernels (pipeline_FaithDiff_tlc.py:101-252, :1324-1409)
+ * --------------------------------------------------------------------------------------------------------- */
+/* grids(): gather T tiles [T, C, k1, k2] (NCHW, any of bf16/fp16/fp32 via elem_bytes) from a canvas [1,C,h,w]. */
+int fd_tile_gather(const void* canvas, void* tiles, const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h,
+                   int32_t w, int32_t k1, int32_t k2, int32_t elem_bytes, void* stream);
+/* grids_inverse(): canvas[1,C,h,w] fp32 = sum_t fp32(fp64(tile_t) * w64) / sum_t w  in row-major tile order,
+ * bit-exact with the reference's fp16/bf16 × fp64 → fp32 accumulation. tile_dtype: 0 bf16, 1 fp16, 2 fp32.    */
+int fd_tile_blend(const void* tiles, int32_t tile_dtype, const double* weights, const int32_t* origins_ij,
+                  int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_f32,
+                  void* canvas_lowp, int32_t lowp_dtype, void* stream);
+/* fused per-step tail: CFG combine + Euler step per tile (diffusers rounding order) + Gaussian blend + cast
+ * + re-tile + scale_model_input for the next step.  eps: UNet outputs NCHW [T,2,C,k1,k2] (uncond, text),
+ * x_tiles: current latents [T,C,k1,k2] (lowp).  Writes canvas_f32, canvas_lowp, next_tiles, next_scaled.     */
+int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, const double* weights,
+                       const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1,
+                       int32_t k2, float guidance, float sigma, float sigma_next, float next_scale_div,
+                       float* canvas_f32, void* canvas_lowp, void* next_tiles, void* next_scaled, void* stream);
+/* accumulate-only variant for the multi-GPU path: adds this rank's tiles (weighted) into a zeroed fp32 canvas
+ * (numerator only); after the all-reduce fd_canvas_finalize divides by the static count map.                 */
+int fd_tile_accumulate(const void* tiles, int32_t tile_dtype, const double* weights, const int32_t* origins_ij,
+                       int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num,
+                       void* stream);
+int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
+                       int32_t lowp_dtype, int64_t n, void* stream);
+/* VAE / LQ-encoder seam blend (Encoder.blend_v/blend_h, …extension.py:150-162): in-place linear cross-fade of
+ * the first `extent` rows (vertical=1) or columns of b with the last `extent` of a; NCHW, dtype 0/1/2.        */
+int fd_seam_blend(const void* a, void* b, int32_t dtype, int32_t c, int32_t ah, int32_t aw, int32_t bh, int32_t bw,
+                  int32_t extent, int32_t vertical, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Image pre/post and colour fix
+ * --------------------------------------------------------------------------------------------------------- */
+/* VaeImageProcessor.preprocess: u8 HWC → NHWC bf16 in [-1,1] ((x/255)*2-1 in fp32) (pipeline…:1246)         */
+int fd_image_preprocess(const uint8_t* rgb_u8, void* out_nhwc_bf16, void* out_nchw_f32_or_null, int32_t h, int32_t w,
+                        void* stream);
+/* VaeImageProcessor.postprocess: NHWC bf16 (c=3) → u8 HWC: round(clamp(x/2+0.5,0,1)*255) (pipeline…:1451)   */
+int fd_image_postprocess(const void* x, int32_t x_is_nhwc_bf16, uint8_t* rgb_u8, int32_t h, int32_t w, void* stream);
+/* utils/color_fix.py:14-27 adain_color_fix and :29-42 wavelet_color_fix on u8 HWC images (fp32 math).
+ * work: fp32 scratch of fd_colorfix_work_floats(h, w) elements.                                              */
+int64_t fd_colorfix_work_floats(int32_t h, int32_t w);
+int fd_adain_color_fix(const uint8_t* target, const uint8_t* source, uint8_t* out, int32_t h, int32_t w, float* work,
+                       void* stream);
+int fd_wavelet_color_fix(const uint8_t* target, const uint8_t* source, uint8_t* out, int32_t h, int32_t w, float* work,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
