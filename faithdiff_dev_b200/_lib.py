@@ -15,7 +15,7 @@ class GemmDesc(C.Structure):
         ("a", C.c_void_p * 2), ("a_cols", C.c_int64 * 2), ("a_ld", C.c_int64 * 2), ("b", C.c_void_p),
         ("M", C.c_int64), ("N", C.c_int64), ("mode", C.c_int32), ("batch", C.c_int32), ("in_h", C.c_int32),
         ("in_w", C.c_int32), ("pad_lo", C.c_int32), ("act", C.c_int32), ("bias_along_m", C.c_int32),
-        ("out_fp32", C.c_int32), ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rows_per_batch", C.c_int64),
+        ("out_fp32", C.c_int32), ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rows_per_batch", C.c_int64), ("ld_rowbias", C.c_int64),
         ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("alpha", C.c_float), ("block_n", C.c_int32),
     ]
@@ -40,21 +40,23 @@ _SIGS = {
     "fd_gemm": [C.POINTER(GemmDesc), vp],
     "fd_attention_d64": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
     "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
-    "fd_groupnorm_work_floats": [i32, i32],
+    "fd_groupnorm_work_floats": [i32, i32, i32],
     "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "fd_layernorm": [vp, vp, vp, vp, i64, i32, f32, vp],
-    "fd_upsample2x_nhwc": [vp, vp, i32, i32, i32, i32, vp],
+    "fd_upsample_nearest_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "fd_nchw_to_nhwc": [vp, i32, vp, i32, i32, i64, vp],
     "fd_nhwc_to_nchw": [vp, vp, i32, i32, i32, i64, vp],
-    "fd_conv3x3_small": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-    "fd_linear_smallm": [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
-    "fd_timestep_embedding": [vp, vp, i32, i32, i64, vp],
-    "fd_batch_axis_attention": [vp, vp, i32, i64, i32, i32, vp],
+    "fd_conv3x3_small": [vp, i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp],
+    "fd_conv1x1_small": [vp, i32, vp, vp, vp, i32, i32, i32, i32, i64, f32, vp],
+    "fd_linear_smallm": [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp],
+    "fd_timestep_embedding": [vp, vp, i32, i32, i32, i64, vp],
+    "fd_batch_axis_attention": [vp, vp, i32, i32, i64, i32, i32, vp],
     "fd_tile_gather": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "fd_tile_blend": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "fd_cfg_euler_blend": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp],
-    "fd_tile_accumulate": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "fd_tile_accumulate": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
     "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
+    "fd_scale_div": [vp, vp, i32, f32, i64, vp],
     "fd_seam_blend": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "fd_image_preprocess": [vp, vp, vp, i32, i32, vp],
     "fd_image_postprocess": [vp, i32, vp, i32, i32, vp],

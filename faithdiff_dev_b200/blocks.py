@@ -1,0 +1,196 @@
+"""Host-side building blocks shared by the UNet, the LQ encoder and the VAE.  Each block owns weights already
+packed into the kernel layouts (bf16 K-major GEMM operands, fp32 biases / norm affine) and drives the C-ABI
+kernels over NHWC bf16 activations.  State-dict keys are the reference's (diffusers 0.28 naming)."""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+class Weights:
+    """Reads tensors of a reference-layout state dict and packs them for the kernels."""
+
+    def __init__(self, sd, device, prefix=""):
+        self.sd, self.device, self.prefix = sd, device, prefix
+        self.used = set()
+
+    def sub(self, p):
+        w = Weights(self.sd, self.device, self.prefix + p)
+        w.used = self.used
+        return w
+
+    def has(self, k):
+        return self.prefix + k in self.sd
+
+    def raw(self, k):
+        self.used.add(self.prefix + k)
+        return self.sd[self.prefix + k]
+
+    def f32(self, k):
+        return self.raw(k).detach().to(self.device, torch.float32).contiguous()
+
+    def mat(self, k):
+        return self.raw(k).detach().to(self.device, BF16).contiguous()
+
+    def conv3(self, k):
+        """[O,I,3,3] -> [O, 9*I] (tap-major, channel-minor)."""
+        w = self.raw(k).detach().to(self.device)
+        return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(BF16).contiguous()
+
+    def conv1(self, k):
+        w = self.raw(k).detach().to(self.device)
+        return w.reshape(w.shape[0], w.shape[1]).to(BF16).contiguous()
+
+
+class ResnetBlock:
+    """diffusers ResnetBlock2D: GN→SiLU→conv3x3(+temb)→GN→SiLU→conv3x3, 1x1 shortcut when channels change."""
+
+    def __init__(self, W, groups, eps, temb_offset=None):
+        self.groups, self.eps = groups, eps
+        self.n1g, self.n1b = W.f32("norm1.weight"), W.f32("norm1.bias")
+        self.c1w, self.c1b = W.conv3("conv1.weight"), W.f32("conv1.bias")
+        self.n2g, self.n2b = W.f32("norm2.weight"), W.f32("norm2.bias")
+        self.c2w, self.c2b = W.conv3("conv2.weight"), W.f32("conv2.bias")
+        self.cout = self.c1w.shape[0]
+        self.temb_offset = temb_offset
+        if W.has("time_emb_proj.weight"):
+            self.tw, self.tb = W.mat("time_emb_proj.weight"), W.f32("time_emb_proj.bias")
+        else:
+            self.tw = None
+        if W.has("conv_shortcut.weight"):
+            self.sw, self.sb = W.conv1("conv_shortcut.weight"), W.f32("conv_shortcut.bias")
+        else:
+            self.sw = None
+
+    def __call__(self, x, temb_all=None, x2=None):
+        B, H, Wd = x.shape[:3]
+        n1 = ops.groupnorm(x, self.n1g, self.n1b, self.groups, self.eps, True, x2=x2)
+        rb = None
+        if self.tw is not None:
+            rb = temb_all[:, self.temb_offset:self.temb_offset + self.cout]
+        h = ops.conv3x3(n1, self.c1w, bias=self.c1b, rowbias=rb)
+        n2 = ops.groupnorm(h, self.n2g, self.n2b, self.groups, self.eps, True)
+        if self.sw is not None:
+            M = B * H * Wd
+            res = ops.gemm(x.reshape(M, -1), self.sw, a2=None if x2 is None else x2.reshape(M, -1), bias=self.sb)
+            res = res.view(B, H, Wd, -1)
+        else:
+            assert x2 is None
+            res = x
+        return ops.conv3x3(n2, self.c2w, bias=self.c2b, residual=res)
+
+
+class VaeAttention:
+    """diffusers Attention in the VAE mid block: GroupNorm, 1 head with d = C (512), q/k/v/out with bias, residual.
+    d=512 does not fit the d64 flash kernel: scores and P·V run as tensor-core GEMMs around a row-softmax kernel."""
+
+    def __init__(self, W, groups, eps):
+        self.groups, self.eps = groups, eps
+        self.ng, self.nb = W.f32("group_norm.weight"), W.f32("group_norm.bias")
+        self.wq, self.bq = W.mat("to_q.weight"), W.f32("to_q.bias")
+        self.wk, self.bk = W.mat("to_k.weight"), W.f32("to_k.bias")
+        self.wv, self.bv = W.mat("to_v.weight"), W.f32("to_v.bias")
+        self.wo, self.bo = W.mat("to_out.0.weight"), W.f32("to_out.0.bias")
+
+    def __call__(self, x):
+        B, H, Wd, Cc = x.shape
+        L = H * Wd
+        n = ops.groupnorm(x, self.ng, self.nb, self.groups, self.eps, False)
+        out = torch.empty_like(x)
+        for b in range(B):
+            nb = n[b].reshape(L, Cc)
+            q = ops.gemm(nb, self.wq, bias=self.bq)
+            k = ops.gemm(nb, self.wk, bias=self.bk)
+            vt = ops.gemm(self.wv, nb, bias=self.bv, bias_along_m=True)           # V^T [C, L] = Wv · X^T
+            s = ops.gemm(q, k, out_fp32=True)                                      # [L, L] fp32 scores
+            p = ops.softmax_rows(s, alpha=Cc ** -0.5)
+            del s
+            o = ops.gemm(p, vt)                                                    # [L, C]
+            ops.gemm(o, self.wo, bias=self.bo, residual=x[b].reshape(L, Cc), out=out[b].reshape(L, Cc))
+        return out
+
+
+class Downsample:
+    def __init__(self, W, pad_lo):
+        self.w, self.b, self.pad_lo = W.conv3("conv.weight"), W.f32("conv.bias"), pad_lo
+
+    def __call__(self, x):
+        return ops.conv3x3(x, self.w, bias=self.b, stride=2, pad_lo=self.pad_lo)
+
+
+class Upsample:
+    def __init__(self, W):
+        self.w, self.b = W.conv3("conv.weight"), W.f32("conv.bias")
+
+    def __call__(self, x, size=None):
+        u = ops.upsample_nearest(x) if size is None else ops.upsample_nearest(x, size[0], size[1])
+        return ops.conv3x3(u, self.w, bias=self.b)
+
+
+def interleave_geglu(w, b):
+    """ff.net.0.proj [8C, C]: rows [0,4C) = value, [4C,8C) = gate → interleaved (v0,g0,v1,g1,…) so one accumulator
+    tile holds both halves and the GEMM epilogue emits value·gelu(gate)."""
+    half = w.shape[0] // 2
+    wi = torch.stack([w[:half], w[half:]], dim=1).reshape(w.shape[0], w.shape[1]).contiguous()
+    bi = torch.stack([b[:half], b[half:]], dim=1).reshape(-1).contiguous()
+    return wi, bi
+
+
+class TransformerBlock:
+    """diffusers BasicTransformerBlock: LN→self-attn→+, LN→cross-attn(text)→+, LN→GEGLU FF→+."""
+
+    def __init__(self, W, heads):
+        self.heads = heads
+        self.ln = [(W.f32("norm%d.weight" % i), W.f32("norm%d.bias" % i)) for i in (1, 2, 3)]
+        self.wqkv = torch.cat([W.mat("attn1.to_q.weight"), W.mat("attn1.to_k.weight"), W.mat("attn1.to_v.weight")], 0).contiguous()
+        self.wo1, self.bo1 = W.mat("attn1.to_out.0.weight"), W.f32("attn1.to_out.0.bias")
+        self.wq2 = W.mat("attn2.to_q.weight")
+        self.wkv2 = torch.cat([W.mat("attn2.to_k.weight"), W.mat("attn2.to_v.weight")], 0).contiguous()
+        self.wo2, self.bo2 = W.mat("attn2.to_out.0.weight"), W.f32("attn2.to_out.0.bias")
+        self.wff1, self.bff1 = interleave_geglu(W.mat("ff.net.0.proj.weight"), W.f32("ff.net.0.proj.bias"))
+        self.wff2, self.bff2 = W.mat("ff.net.2.weight"), W.f32("ff.net.2.bias")
+        self.C = self.wo1.shape[0]
+        self.scale = (self.C // heads) ** -0.5
+
+    def text_kv(self, text2d):
+        return ops.gemm(text2d, self.wkv2)
+
+    def __call__(self, h, B, L, kv, lk):
+        Cc = self.C
+        y = ops.layernorm(h, *self.ln[0])
+        qkv = ops.gemm(y, self.wqkv)
+        a = ops.attention(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, self.heads, L, L, self.scale)
+        h = ops.gemm(a, self.wo1, bias=self.bo1, residual=h)
+        y = ops.layernorm(h, *self.ln[1])
+        q = ops.gemm(y, self.wq2)
+        a = ops.attention(q, kv[:, :Cc], kv[:, Cc:], B, self.heads, L, lk, self.scale)
+        h = ops.gemm(a, self.wo2, bias=self.bo2, residual=h)
+        y = ops.layernorm(h, *self.ln[2])
+        g = ops.gemm(y, self.wff1, bias=self.bff1, act=2)
+        return ops.gemm(g, self.wff2, bias=self.bff2, residual=h)
+
+
+class Transformer2D:
+    """diffusers Transformer2DModel (use_linear_projection): GN(eps 1e-6) → Linear in → N blocks → Linear out → + input."""
+
+    def __init__(self, W, heads, groups):
+        self.groups = groups
+        self.ng, self.nb = W.f32("norm.weight"), W.f32("norm.bias")
+        self.wi, self.bi = W.mat("proj_in.weight"), W.f32("proj_in.bias")
+        self.wo, self.bo = W.mat("proj_out.weight"), W.f32("proj_out.bias")
+        self.blocks = []
+        i = 0
+        while W.has("transformer_blocks.%d.norm1.weight" % i):
+            self.blocks.append(TransformerBlock(W.sub("transformer_blocks.%d." % i), heads))
+            i += 1
+
+    def __call__(self, x, kv_list, lk):
+        B, H, Wd, Cc = x.shape
+        L = H * Wd
+        n = ops.groupnorm(x, self.ng, self.nb, self.groups, 1e-6, False)
+        h = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi)
+        for blk, kv in zip(self.blocks, kv_list):
+            h = blk(h, B, L, kv, lk)
+        out = ops.gemm(h, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc))
+        return out.view(B, H, Wd, Cc)

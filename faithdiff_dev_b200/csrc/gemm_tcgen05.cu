@@ -24,7 +24,7 @@ struct GemmKParams {
   // epilogue
   const float* bias;
   const float* rowbias;
-  long long rows_per_batch;
+  long long rows_per_batch, ld_rowbias;
   const __nv_bfloat16* residual;
   long long ld_res;
   void* out;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             }
           }
           if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)sample * p.N + n;
+            const float* rb = p.rowbias + (long long)sample * p.ld_rowbias + n;
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
             x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
@@ -416,6 +416,8 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
                           CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
   }
   p.bias = d->bias; p.rowbias = d->rowbias; p.rows_per_batch = d->rows_per_batch > 0 ? d->rows_per_batch : M;
+  p.ld_rowbias = d->ld_rowbias > 0 ? d->ld_rowbias : d->N;
+  FD_REQUIRE(!d->rowbias || (((uintptr_t)d->rowbias % 16) == 0 && p.ld_rowbias % 4 == 0), "fd_gemm: rowbias alignment");
   p.residual = (const __nv_bfloat16*)d->residual; p.ld_res = d->ld_res;
   p.out = d->out; p.ld_out = d->ld_out; p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   p.act = d->act; p.bias_along_m = d->bias_along_m; p.out_fp32 = d->out_fp32;

@@ -1,0 +1,319 @@
+"""Thin tensor-level wrappers over the C-ABI (include/faithdiff_b200.h).  torch supplies device memory and the
+stream; every call lands in a hand-written sm_100a kernel of libfaithdiff_b200.so.  No fallbacks."""
+import ctypes as C
+
+import torch
+
+from ._lib import GemmDesc, check, lib
+
+BF16 = torch.bfloat16
+_DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _row_view(t):
+    """2-D view requirements: unit inner stride; returns (ptr, cols, pitch)."""
+    assert t.dim() == 2 and t.stride(1) == 1 and t.dtype == BF16, (t.shape, t.stride(), t.dtype)
+    return t.data_ptr(), t.shape[1], t.stride(0)
+
+
+def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None, act=0, out=None, out_fp32=False,
+         alpha=1.0, bias_along_m=False, block_n=0):
+    """out[M,N] = epilogue(alpha * [a | a2] @ w^T).  a/a2: bf16 [M,K*] (unit inner stride); w: bf16 [N,K] contiguous."""
+    d = GemmDesc()
+    d.a[0], d.a_cols[0], d.a_ld[0] = _row_view(a)
+    if a2 is not None:
+        d.a[1], d.a_cols[1], d.a_ld[1] = _row_view(a2)
+    M, N = a.shape[0], w.shape[0]
+    assert w.is_contiguous() and w.dtype == BF16 and w.shape[1] == a.shape[1] + (a2.shape[1] if a2 is not None else 0)
+    n_out = N // 2 if act == 2 else N
+    if out is None:
+        out = torch.empty((M, n_out), device=a.device, dtype=torch.float32 if out_fp32 else BF16)
+    assert out.stride(1) == 1 and out.shape[0] == M and out.shape[1] == n_out
+    d.b, d.M, d.N, d.mode = w.data_ptr(), M, N, 0
+    d.act, d.bias_along_m, d.out_fp32 = act, int(bias_along_m), int(out.dtype == torch.float32)
+    if bias is not None:
+        assert bias.dtype == torch.float32
+        d.bias = bias.data_ptr()
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32 and rowbias.stride(1) == 1
+        d.rowbias, d.rows_per_batch, d.ld_rowbias = rowbias.data_ptr(), rows_per_batch, rowbias.stride(0)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.stride(1) == 1
+        d.residual, d.ld_res = residual.data_ptr(), residual.stride(0)
+    d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(0), alpha, block_n
+    check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm")
+    return out
+
+
+def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None):
+    """3x3 conv on NHWC bf16 x [B,H,W,C] (optionally channel-concatenated with x2); w packed [N, 9*(C+C2)]."""
+    assert x.dim() == 4 and x.dtype == BF16 and x.stride(3) == 1
+    B, H, W, C0 = x.shape
+    assert x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1), "NHWC images must be dense in B,H,W"
+    d = GemmDesc()
+    d.a[0], d.a_cols[0], d.a_ld[0] = x.data_ptr(), C0, x.stride(2)
+    ct = C0
+    if x2 is not None:
+        assert x2.shape[:3] == x.shape[:3] and x2.stride(3) == 1
+        d.a[1], d.a_cols[1], d.a_ld[1] = x2.data_ptr(), x2.shape[3], x2.stride(2)
+        ct += x2.shape[3]
+    N = w.shape[0]
+    assert w.is_contiguous() and w.shape[1] == 9 * ct, (w.shape, ct)
+    if stride == 1:
+        Ho, Wo = H, W
+    else:
+        Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pad_lo else ((H - 2) // 2 + 1, (W - 2) // 2 + 1)
+    if out is None:
+        out = torch.empty((B, Ho, Wo, N), device=x.device, dtype=BF16)
+    assert out.stride(3) == 1 and out.stride(1) == Wo * out.stride(2) and out.stride(0) == Ho * out.stride(1)
+    d.b, d.N, d.mode, d.batch, d.in_h, d.in_w, d.pad_lo = w.data_ptr(), N, 1 if stride == 1 else 2, B, H, W, pad_lo
+    d.act = act
+    if bias is not None:
+        d.bias = bias.data_ptr()
+    if rowbias is not None:
+        assert rowbias.dtype == torch.float32 and rowbias.stride(1) == 1 and rowbias.shape[0] == B
+        d.rowbias, d.ld_rowbias = rowbias.data_ptr(), rowbias.stride(0)
+    if residual is not None:
+        assert residual.dtype == BF16 and residual.stride(3) == 1
+        d.residual, d.ld_res = residual.data_ptr(), residual.stride(2)
+    d.out, d.ld_out, d.alpha = out.data_ptr(), out.stride(2), 1.0
+    check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(conv)")
+    return out
+
+
+def attention(q, k, v, batch, heads, lq, lk, scale, out=None):
+    """q [batch*lq, >=heads*64] / k, v [batch*lk, ...] bf16 row views (unit inner stride) -> out [batch*lq, heads*64]."""
+    if out is None:
+        out = torch.empty((batch * lq, heads * 64), device=q.device, dtype=BF16)
+    check(lib.fd_attention_d64(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), batch,
+                               heads, lq, lk, scale, _stream()), "fd_attention_d64")
+    return out
+
+
+def softmax_rows(s, alpha=1.0):
+    p = torch.empty(s.shape, device=s.device, dtype=BF16)
+    check(lib.fd_softmax_rows(_p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], s.shape[1], alpha, _stream()),
+          "fd_softmax_rows")
+    return p
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu, x2=None, out=None):
+    """GroupNorm(+SiLU) on NHWC bf16 [B,H,W,C] (contiguous); x2 concatenates along C."""
+    assert x.is_contiguous() and x.dtype == BF16 and (x2 is None or x2.is_contiguous())
+    B, C0 = x.shape[0], x.shape[-1]
+    c1 = x2.shape[-1] if x2 is not None else 0
+    hw = x.numel() // (B * C0)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (C0 + c1,), device=x.device, dtype=BF16)
+    work = torch.empty(lib.fd_groupnorm_work_floats(B, groups, C0 + c1), device=x.device, dtype=torch.float32)
+    check(lib.fd_groupnorm_nhwc(_p(x), C0, _p(x2), c1, _p(gamma), _p(beta), _p(out), B, hw, groups, eps, int(silu),
+                                _p(work), _stream()), "fd_groupnorm_nhwc")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    assert x.is_contiguous() and x.dtype == BF16
+    if out is None:
+        out = torch.empty_like(x)
+    cols = x.shape[-1]
+    check(lib.fd_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // cols, cols, eps, _stream()), "fd_layernorm")
+    return out
+
+
+def upsample_nearest(x, oh=None, ow=None):
+    B, H, W, Cc = x.shape
+    oh, ow = oh or 2 * H, ow or 2 * W
+    out = torch.empty((B, oh, ow, Cc), device=x.device, dtype=BF16)
+    check(lib.fd_upsample_nearest_nhwc(_p(x), _p(out), B, H, W, oh, ow, Cc, _stream()), "fd_upsample_nearest_nhwc")
+    return out
+
+
+def nchw_to_nhwc(x):
+    assert x.is_contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, Cc), device=x.device, dtype=BF16)
+    check(lib.fd_nchw_to_nhwc(_p(x), _DT[x.dtype], _p(out), B, Cc, H * W, _stream()), "fd_nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, dtype=BF16):
+    assert x.is_contiguous() and x.dtype == BF16
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), device=x.device, dtype=dtype)
+    check(lib.fd_nhwc_to_nchw(_p(x), _p(out), _DT[dtype], B, Cc, H * W, _stream()), "fd_nhwc_to_nchw")
+    return out
+
+
+_IN_MODE = {torch.bfloat16: 1, torch.float32: 2, torch.float16: 3}
+
+
+def conv3x3_small_in(x_nchw_or_nhwc, w, bias, nhwc_in=False, out=None):
+    """cin <= 8. x: NCHW (bf16/fp16/fp32) or NHWC bf16 -> NHWC bf16 [B,H,W,cout] (out may be a channel-slice view)."""
+    x = x_nchw_or_nhwc
+    assert x.is_contiguous()
+    if nhwc_in:
+        B, H, W, cin = x.shape
+        mode = 0
+    else:
+        B, cin, H, W = x.shape
+        mode = _IN_MODE[x.dtype]
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W, cout), device=x.device, dtype=BF16)
+    check(lib.fd_conv3x3_small(_p(x), mode, _p(w), _p(bias), _p(out), 0, out.stride(2), B, H, W, cin, cout, _stream()),
+          "fd_conv3x3_small(in)")
+    return out
+
+
+def conv3x3_small_out(x, w, bias, out_dtype=BF16, nchw_out=True):
+    """cout <= 8. x NHWC bf16 -> NCHW out_dtype (or NHWC bf16)."""
+    assert x.is_contiguous() and x.dtype == BF16
+    B, H, W, cin = x.shape
+    cout = w.shape[0]
+    if nchw_out:
+        out = torch.empty((B, cout, H, W), device=x.device, dtype=out_dtype)
+        mode = _IN_MODE[out_dtype]
+    else:
+        out = torch.empty((B, H, W, cout), device=x.device, dtype=BF16)
+        mode = 0
+    check(lib.fd_conv3x3_small(_p(x), 0, _p(w), _p(bias), _p(out), mode, 0, B, H, W, cin, cout, _stream()),
+          "fd_conv3x3_small(out)")
+    return out
+
+
+def conv1x1_small(x, w, bias, out_dtype=None, in_scale=1.0):
+    assert x.is_contiguous()
+    B, cin, H, W = x.shape
+    cout = w.shape[0]
+    out = torch.empty((B, cout, H, W), device=x.device, dtype=out_dtype or x.dtype)
+    check(lib.fd_conv1x1_small(_p(x), _DT[x.dtype], _p(w), _p(bias), _p(out), _DT[out.dtype], B, cin, cout, H * W,
+                               in_scale, _stream()), "fd_conv1x1_small")
+    return out
+
+
+def linear_smallm(x, w, bias=None, addend=None, silu_in=False, silu_out=False):
+    assert x.dtype == torch.float32 and x.is_contiguous() and w.dtype == BF16 and w.is_contiguous()
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=torch.float32)
+    for m0 in range(0, M, 8):
+        m = min(8, M - m0)
+        check(lib.fd_linear_smallm(_p(x[m0:]), _p(w), _p(bias), _p(addend[m0:]) if addend is not None else None,
+                                   _p(out[m0:]), m, N, K, int(silu_in), int(silu_out), _stream()), "fd_linear_smallm")
+    return out
+
+
+def timestep_embedding(values, dim, out=None, inner=1, outer_ld=None):
+    assert values.dtype == torch.float32 and values.is_contiguous()
+    n = values.numel()
+    if out is None:
+        out = torch.empty((n, dim), device=values.device, dtype=torch.float32)
+        outer_ld = dim
+    check(lib.fd_timestep_embedding(_p(values), _p(out), n, dim, inner, outer_ld, _stream()), "fd_timestep_embedding")
+    return out
+
+
+def batch_axis_attention(qkv, groups, seq, hw, embed, heads):
+    out = torch.empty((groups * seq * hw, embed), device=qkv.device, dtype=BF16)
+    check(lib.fd_batch_axis_attention(_p(qkv), _p(out), groups, seq, hw, embed, heads, _stream()), "fd_batch_axis_attention")
+    return out
+
+
+# ------------------------------------------------------------------ tiled latents
+def tile_gather(canvas, origins, k1, k2):
+    _, c, h, w = canvas.shape
+    T = origins.shape[0]
+    tiles = torch.empty((T, c, k1, k2), device=canvas.device, dtype=canvas.dtype)
+    check(lib.fd_tile_gather(_p(canvas), _p(tiles), _p(origins), T, c, h, w, k1, k2, canvas.element_size(), _stream()),
+          "fd_tile_gather")
+    return tiles
+
+
+def tile_blend(tiles, weights, origins, h, w, lowp_dtype=None):
+    T, c, k1, k2 = tiles.shape
+    canvas = torch.empty((1, c, h, w), device=tiles.device, dtype=torch.float32)
+    lowp = torch.empty((1, c, h, w), device=tiles.device, dtype=lowp_dtype) if lowp_dtype is not None else None
+    check(lib.fd_tile_blend(_p(tiles), _DT[tiles.dtype], _p(weights), _p(origins), T, c, h, w, k1, k2, _p(canvas), _p(lowp),
+                            _DT[lowp_dtype] if lowp_dtype is not None else 0, _stream()), "fd_tile_blend")
+    return canvas, lowp
+
+
+def cfg_euler_blend(eps, x_tiles, weights, origins, h, w, guidance, sigma, sigma_next, next_div, want_next=True):
+    T, c, k1, k2 = x_tiles.shape
+    dev, dt = x_tiles.device, x_tiles.dtype
+    canvas = torch.empty((1, c, h, w), device=dev, dtype=torch.float32)
+    lowp = torch.empty((1, c, h, w), device=dev, dtype=dt)
+    nxt = torch.empty_like(x_tiles) if want_next else None
+    nxs = torch.empty_like(x_tiles) if want_next else None
+    check(lib.fd_cfg_euler_blend(_p(eps), _p(x_tiles), _DT[dt], _p(weights), _p(origins), T, c, h, w, k1, k2, guidance, sigma,
+                                 sigma_next, next_div, _p(canvas), _p(lowp), _p(nxt), _p(nxs), _stream()), "fd_cfg_euler_blend")
+    return canvas, lowp, nxt, nxs
+
+
+def tile_accumulate(tiles, eps, weights, origins, canvas_num, guidance=0.0, sigma=1.0, sigma_next=1.0):
+    T, c, k1, k2 = tiles.shape
+    _, _, h, w = canvas_num.shape
+    check(lib.fd_tile_accumulate(_p(tiles), _p(eps), _DT[tiles.dtype], _p(weights), _p(origins), T, c, h, w, k1, k2, guidance,
+                                 sigma, sigma_next, _p(canvas_num), _stream()), "fd_tile_accumulate")
+
+
+def canvas_finalize(num, count, lowp_dtype):
+    out = torch.empty_like(num)
+    lowp = torch.empty(num.shape, device=num.device, dtype=lowp_dtype)
+    check(lib.fd_canvas_finalize(_p(num), _p(count), _p(out), _p(lowp), _DT[lowp_dtype], num.numel(), _stream()),
+          "fd_canvas_finalize")
+    return out, lowp
+
+
+def scale_div(x, div):
+    out = torch.empty_like(x)
+    check(lib.fd_scale_div(_p(x), _p(out), _DT[x.dtype], div, x.numel(), _stream()), "fd_scale_div")
+    return out
+
+
+def seam_blend(a, b, extent, vertical):
+    """In-place on b. a, b: [1,C,H,W] contiguous."""
+    assert a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype
+    check(lib.fd_seam_blend(_p(a), _p(b), _DT[a.dtype], a.shape[1], a.shape[2], a.shape[3], b.shape[2], b.shape[3], extent,
+                            int(vertical), _stream()), "fd_seam_blend")
+    return b
+
+
+# ------------------------------------------------------------------ image / colour fix
+def image_preprocess(rgb_u8, want_nchw_f32=False):
+    h, w, _ = rgb_u8.shape
+    nhwc = torch.empty((1, h, w, 3), device=rgb_u8.device, dtype=BF16)
+    nchw = torch.empty((1, 3, h, w), device=rgb_u8.device, dtype=torch.float32) if want_nchw_f32 else None
+    check(lib.fd_image_preprocess(_p(rgb_u8), _p(nhwc), _p(nchw), h, w, _stream()), "fd_image_preprocess")
+    return nhwc, nchw
+
+
+def image_postprocess(x, nhwc_bf16=True):
+    if nhwc_bf16:
+        _, h, w, _ = x.shape
+    else:
+        _, _, h, w = x.shape
+    out = torch.empty((h, w, 3), device=x.device, dtype=torch.uint8)
+    check(lib.fd_image_postprocess(_p(x), int(nhwc_bf16), _p(out), h, w, _stream()), "fd_image_postprocess")
+    return out
+
+
+def color_fix(target_u8, source_u8, mode):
+    h, w, _ = target_u8.shape
+    out = torch.empty_like(target_u8)
+    work = torch.empty(lib.fd_colorfix_work_floats(h, w), device=target_u8.device, dtype=torch.float32)
+    fn = lib.fd_adain_color_fix if mode == "adain" else lib.fd_wavelet_color_fix
+    check(fn(_p(target_u8), _p(source_u8), _p(out), h, w, _p(work), _stream()), "fd_%s_color_fix" % mode)
+    return out
+
+
+def launch_count():
+    return int(lib.fd_launch_count())

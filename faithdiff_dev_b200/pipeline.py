@@ -1,0 +1,261 @@
+"""B200-native drop-in for `FaithDiffStableDiffusionXLPipeline` (FaithDiff/pipelines/pipeline_FaithDiff_tlc.py:374-1459):
+same constructor components and `__call__` signature, same tile layout / blend / scheduler semantics; the hot loop is
+re-organised for the hardware (step-invariant work hoisted, CFG-identical stem evaluated once, per-step host logic
+reduced to three scalars, the whole per-step tail fused into one kernel, tiles sharded over ranks with one NCCL
+all-reduce of the fp32 overlap accumulation per scheduler step)."""
+from dataclasses import dataclass
+from typing import List, Optional, Union
+
+import numpy as np
+import PIL.Image
+import torch
+
+from . import ops
+from .blocks import BF16
+from .tiling import LocalAttention, gaussian_weights, tile_origins
+
+
+@dataclass
+class FaithDiffStableDiffusionXLPipelineOutput:
+    """FaithDiff/pipelines/pipeline_output.py:10-21."""
+    images: Union[List[PIL.Image.Image], np.ndarray]
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+class FaithDiffStableDiffusionXLPipeline:
+    model_cpu_offload_seq = "text_encoder->text_encoder_2->denoise_encoder->unet->vae"
+
+    def __init__(self, vae, denoise_encoder, text_encoder, text_encoder_2, tokenizer, tokenizer_2, unet, scheduler,
+                 DDPM_scheduler, force_zeros_for_empty_prompt=True, add_watermarker=None):
+        self.vae, self.denoise_encoder = vae, denoise_encoder
+        self.text_encoder, self.text_encoder_2 = text_encoder, text_encoder_2
+        self.tokenizer, self.tokenizer_2 = tokenizer, tokenizer_2
+        self.unet, self.scheduler, self.DDPM_scheduler = unet, scheduler, DDPM_scheduler
+        self.config = _Cfg(force_zeros_for_empty_prompt=force_zeros_for_empty_prompt)
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+        self.default_sample_size = self.unet.config.sample_size
+        self.watermark = None
+        self.device = torch.device("cuda")
+        self.rank, self.world_size, self.process_group = 0, 1, None
+        self.timings = {}
+
+    # ------------------------------------------------------------------ reference-facing knobs
+    def to(self, device=None, *a, **k):
+        if device is not None and torch.device(device).type != "cuda":
+            raise RuntimeError("faithdiff_dev_b200 has no CPU path")
+        return self
+
+    def set_progress_bar_config(self, **kw):
+        pass
+
+    def enable_model_cpu_offload(self, *a, **k):
+        raise NotImplementedError("cpu offload is not supported: the B200 path keeps all weights resident in HBM")
+
+    def set_encoder_tile_settings(self, denoise_encoder_tile_sample_min_size=1024, denoise_encoder_sample_overlap_factor=0.25,
+                                  vae_sample_size=1024, vae_tile_overlap_factor=0.25):
+        """pipeline…:888-896 (including the quirk that vae.config.sample_size does not retune the VAE tile size)."""
+        self.denoise_encoder.tile_sample_min_size = denoise_encoder_tile_sample_min_size
+        self.denoise_encoder.tile_overlap_factor = denoise_encoder_sample_overlap_factor
+        self.vae.config.sample_size = vae_sample_size
+        self.vae.tile_overlap_factor = vae_tile_overlap_factor
+
+    def enable_vae_tiling(self):
+        self.vae.enable_tiling()
+        self.denoise_encoder.enable_tiling()
+
+    def disable_vae_tiling(self):
+        self.vae.disable_tiling()
+        self.denoise_encoder.disable_tiling()
+
+    def set_distributed(self, rank, world_size, process_group=None):
+        """Multi-GPU: tiles are sharded round-robin over ranks; one all-reduce of the fp32 canvas per step."""
+        self.rank, self.world_size, self.process_group = rank, world_size, process_group
+
+    def check_inputs(self, lr_img, prompt, height, width, prompt_embeds, negative_prompt, negative_prompt_embeds,
+                     pooled_prompt_embeds, negative_pooled_prompt_embeds):
+        """pipeline…:737-817 (the rules that apply to this call path)."""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError("Cannot forward both `prompt` and `prompt_embeds`. Please make sure to only forward one of the two.")
+        if prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` undefined.")
+        if prompt is not None and not isinstance(prompt, (str, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError("Cannot forward both `negative_prompt` and `negative_prompt_embeds`.")
+        if prompt_embeds is not None and pooled_prompt_embeds is None:
+            raise ValueError("If `prompt_embeds` are provided, `pooled_prompt_embeds` also have to be passed.")
+        if negative_prompt_embeds is not None and negative_pooled_prompt_embeds is None:
+            raise ValueError("If `negative_prompt_embeds` are provided, `negative_pooled_prompt_embeds` also have to be passed.")
+
+    def encode_prompt(self, prompt, negative_prompt=None, **kw):
+        """Prompt encoding (pipeline…:485-717) is the caller immediately before the hot path (SURVEY §8f rank 1,
+        'next'): it needs the CLIP text encoders + tokenizers, which are torch/transformers modules outside this
+        round's scope.  Pass prompt_embeds / pooled_prompt_embeds (the reference accepts but ignores them)."""
+        raise NotImplementedError("encode_prompt: pass prompt_embeds/negative_prompt_embeds/pooled_prompt_embeds/"
+                                  "negative_pooled_prompt_embeds; the CLIP text encoders are not part of the B200 hot path yet")
+
+    # ------------------------------------------------------------------ stages
+    def _preprocess(self, lr_img, height, width):
+        """VaeImageProcessor.preprocess (pipeline…:1246): host u8 → pinned → H2D → kernel."""
+        if isinstance(lr_img, PIL.Image.Image):
+            w, h = width - width % 8, height - height % 8
+            if lr_img.size != (w, h):
+                lr_img = lr_img.resize((w, h), resample=PIL.Image.LANCZOS)
+            arr = np.asarray(lr_img.convert("RGB"), dtype=np.uint8)
+            host = torch.from_numpy(np.ascontiguousarray(arr))
+        else:
+            host = lr_img            # HWC uint8 tensor (host, ideally pinned)
+        if not host.is_cuda:
+            if not host.is_pinned():
+                host = host.pin_memory()
+            self._h2d_bytes = host.numel()
+            dev = host.to(self.device, non_blocking=True)
+        else:
+            self._h2d_bytes = 0
+            dev = host
+        nhwc, _ = ops.image_preprocess(dev)
+        return nhwc, dev
+
+    def _encode_lq(self, lr_nhwc):
+        """prepare_image_latents (pipeline…:950-1004) → denoise_encoder (LQ features), NHWC bf16 [1,h,w,512]."""
+        enc = self.denoise_encoder
+        x_nchw = ops.nhwc_to_nchw(lr_nhwc, BF16)
+        feats = enc(x_nchw)
+        return ops.nchw_to_nhwc(feats.contiguous()), x_nchw
+
+    @torch.no_grad()
+    def __call__(self, lr_img=None, prompt=None, prompt_2=None, height=None, width=None, num_inference_steps=50,
+                 start_point="noise", timesteps=None, denoising_end=None, overlap=0.5, guidance_scale=5.0,
+                 negative_prompt=None, negative_prompt_2=None, num_images_per_prompt=1, eta=0.0, generator=None,
+                 latents=None, prompt_embeds=None, negative_prompt_embeds=None, pooled_prompt_embeds=None,
+                 negative_pooled_prompt_embeds=None, output_type="pil", return_dict=True, cross_attention_kwargs=None,
+                 guidance_rescale=0.0, original_size=None, target_size=None, clip_skip=None, callback_on_step_end=None,
+                 callback_on_step_end_tensor_inputs=("latents",), add_sample=True, **kwargs):
+        if not torch.cuda.is_available():
+            raise RuntimeError("faithdiff_dev_b200 has no CPU path: a CUDA device is required")
+        if timesteps is not None or denoising_end is not None or cross_attention_kwargs or guidance_rescale:
+            raise NotImplementedError("custom timesteps / denoising_end / cross_attention_kwargs / guidance_rescale")
+        if guidance_scale <= 1:
+            raise NotImplementedError("the hot path implements the classifier-free-guidance branch (guidance_scale > 1)")
+        height = height or self.default_sample_size * self.vae_scale_factor
+        width = width or self.default_sample_size * self.vae_scale_factor
+        original_size = original_size or (height, width)
+        target_size = target_size or (height, width)
+        self.check_inputs(lr_img, prompt, height, width, prompt_embeds, negative_prompt, negative_prompt_embeds,
+                          pooled_prompt_embeds, negative_pooled_prompt_embeds)
+        if prompt_embeds is None:
+            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
+                prompt, negative_prompt=negative_prompt)
+        dev, dt = self.device, BF16
+        unet, vae, sch = self.unet, self.vae, self.scheduler
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "enc", "loop", "dec")}
+        ev["t0"].record()
+
+        # -- image → LQ features → tiles (once per image)
+        lr_nhwc, _ = self._preprocess(lr_img, height, width)
+        sch.set_timesteps(num_inference_steps, device="cpu")
+        ts = sch.timesteps
+        lq_nhwc, lr_nchw = self._encode_lq(lr_nhwc)
+        h, w = height // 8, width // 8
+        k = (target_size[0] // 8, target_size[1] // 8)
+        self.tlc_vae_latents = LocalAttention(k, overlap)
+        self.tlc_vae_img = LocalAttention(k, overlap)
+        idx, k1, k2 = tile_origins(h, w, k[0], k[1], overlap)
+        T = len(idx)
+        la = self.tlc_vae_latents
+
+        # -- initial latents (torch RNG on purpose: seeds must reproduce the reference's Philox stream)
+        shape = (1, vae.config.latent_channels, h, w)
+        if latents is None:
+            gdev = generator.device if generator is not None else dev
+            latents = torch.randn(shape, generator=generator, device=gdev, dtype=dt).to(dev)
+        latents = latents.to(dev) * sch.init_noise_sigma
+        if start_point == "lr":
+            z0 = vae.encode(lr_nchw).latent_dist.sample() * vae.config.scaling_factor
+            t0 = torch.randint(999, 1000, (1,), device=dev).long()
+            latents = self.DDPM_scheduler.add_noise(z0[0:1], latents, t0)
+        tiles = la.grids(latents.contiguous())                      # [T,4,k1,k2]
+        weights, origins = la.weights64, la.origins
+
+        # -- step/tile-invariant conditioning
+        pe = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(dev, dt)
+        te = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], dim=0).to(dev, dt)
+        kv, lk = unet.text_kv(pe)
+        mine = [t for t in range(T) if t % self.world_size == self.rank]
+        cond = {}
+        for t in mine:                                              # ControlNetConditioningEmbedding: once per tile
+            i, j = idx[t]
+            cond[t] = unet.condition_embed(lq_nhwc[:, i:i + k1, j:j + k2, :].contiguous())
+        ids_all = torch.tensor([[original_size[0], original_size[1], i, j, target_size[0], target_size[1]] for i, j in idx],
+                               dtype=torch.float32).to(dt).to(torch.float32)   # rounded through the working dtype
+        count = None
+        if self.world_size > 1:
+            count = torch.zeros(shape, device=dev, dtype=torch.float32)
+            ops.tile_accumulate(torch.ones((T, shape[1], k1, k2), device=dev, dtype=torch.float32), None, weights, origins, count)
+        ev["enc"].record()
+
+        # -- denoising loop (pipeline…:1324-1409)
+        s0, _, div0 = sch.step_scalars(0)
+        scaled = ops.scale_div(tiles, div0)
+        eps = torch.empty((T, 2) + tuple(tiles.shape[1:]), device=dev, dtype=dt)
+        canvas_lowp = None
+        for i in range(len(ts)):
+            sigma, sigma_next, _ = sch.step_scalars(i)
+            next_div = sch.step_scalars(i + 1)[2] if i + 1 < len(ts) else 1.0
+            tval = ts[i]
+            for t in mine:
+                ids = ids_all[t:t + 1].repeat(2, 1)
+                temb = unet.time_embeddings(tval, te, ids, 2)
+                x1 = unet.stem(scaled[t:t + 1], cond[t], add_sample=add_sample, groups=1)     # CFG halves identical → once
+                x2 = x1.expand(2, -1, -1, -1).contiguous()
+                eps[t] = unet.trunk(x2, temb, kv, lk, dt)
+            if self.world_size == 1:
+                canvas, canvas_lowp, tiles, scaled = ops.cfg_euler_blend(eps, tiles, weights, origins, h, w, guidance_scale,
+                                                                         sigma, sigma_next, next_div)
+            else:
+                num = torch.zeros(shape, device=dev, dtype=torch.float32)
+                sel = torch.tensor(mine, device=dev)
+                ops.tile_accumulate(tiles[sel].contiguous(), eps[sel].contiguous(), weights, origins[sel].contiguous(), num,
+                                    guidance_scale, sigma, sigma_next)
+                torch.distributed.all_reduce(num, group=self.process_group)
+                canvas, canvas_lowp = ops.canvas_finalize(num, count, dt)
+                tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)
+                scaled = ops.scale_div(tiles, next_div)
+            if callback_on_step_end is not None:
+                callback_on_step_end(self, i, tval, {"latents": canvas_lowp})
+        latents = canvas_lowp
+        ev["loop"].record()
+        if output_type == "latent":
+            image = latents
+        else:
+            # -- decode (pipeline…:1411-1451): latents / scaling_factor → VAE → u8
+            z = latents / vae.config.scaling_factor
+            image = vae.decode(z, return_dict=False)[0]
+            u8 = ops.image_postprocess(ops.nchw_to_nhwc(image.contiguous()), True)
+            self._last_u8 = u8
+            if output_type == "pil":
+                host = torch.empty(u8.shape, dtype=torch.uint8, pin_memory=True)
+                host.copy_(u8, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self._d2h_bytes = host.numel()
+                image = [PIL.Image.fromarray(host.numpy())]
+            elif output_type == "u8":
+                image = [u8]
+            else:
+                image = ops.nchw_to_nhwc(image.contiguous())
+        ev["dec"].record()
+        self._events = ev
+        if not return_dict:
+            return (image,)
+        return FaithDiffStableDiffusionXLPipelineOutput(images=image)
+
+    def stage_times_ms(self):
+        e = self._events
+        torch.cuda.synchronize()
+        return {"encode": e["t0"].elapsed_time(e["enc"]), "denoise": e["enc"].elapsed_time(e["loop"]),
+                "decode": e["loop"].elapsed_time(e["dec"])}

@@ -47,6 +47,7 @@ typedef struct fd_gemm_desc {
   const float* bias;     /* [N] (or [M]) fp32, or NULL                                                    */
   const float* rowbias;  /* [M / rows_per_batch, N] fp32 added per sample (timestep embedding), or NULL   */
   int64_t rows_per_batch;
+  int64_t ld_rowbias;    /* row pitch of rowbias in floats (0 → N)                                        */
   const void* residual;  /* bf16 [M, ld_res] added after the activation, or NULL                          */
   int64_t ld_res;
   void* out;             /* [M, ld_out]                                                                   */
@@ -74,10 +75,10 @@ int fd_softmax_rows(const float* s, int64_t ld_s, void* p, int64_t ld_p, int64_t
  * Bandwidth-bound kernels (NHWC bf16 activations)
  * --------------------------------------------------------------------------------------------------------- */
 /* GroupNorm(+SiLU) over the channel-concatenation of up to two NHWC sources → one NHWC output [B,HW,C0+C1].
- * work: fp32 scratch of fd_groupnorm_work_floats(batch, groups) elements.
+ * work: fp32 scratch of fd_groupnorm_work_floats(batch, groups, c0+c1) elements.
  * Replaces: ResnetBlock2D.norm1/norm2 + SiLU, Transformer2DModel.norm, conv_norm_out (…extension.py:688-689),
  * ControlNetConditioningEmbedding.norm_in (:215), torch.cat of skip connections in the up blocks.          */
-int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups);
+int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups, int32_t channels);
 int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
                       void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
                       void* stream);
@@ -85,26 +86,36 @@ int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, co
  * FaithDiff LayerNorm (…extension.py:229-235).                                                             */
 int fd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int32_t cols, float eps,
                  void* stream);
-/* nearest 2x upsample NHWC (Upsample2D before its conv) */
-int fd_upsample2x_nhwc(const void* x, void* out, int32_t batch, int32_t h, int32_t w, int32_t c, void* stream);
+/* nearest-neighbour resize NHWC (Upsample2D before its conv: oh=2h, ow=2w, or the `upsample_size` path) */
+int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch, int32_t h, int32_t w, int32_t oh, int32_t ow,
+                             int32_t c, void* stream);
 /* NCHW <-> NHWC layout changes at the module boundary (the reference's forward signatures are NCHW). in_dtype /
  * out_dtype: 0 bf16, 1 fp16, 2 fp32.                                                                       */
 int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out_bf16, int32_t batch, int32_t c, int64_t hw, void* stream);
 int fd_nhwc_to_nchw(const void* x_bf16, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream);
-/* direct 3x3 convs with a tiny channel count on one side (conv_in 4→C, conv_out C→4, VAE 3→128 / 128→3):
- * x NHWC bf16 [B,H,W,cin], w bf16 [cout, 9*cin] (tap-major), out NHWC bf16.                                 */
-int fd_conv3x3_small(const void* x, const void* w, const float* bias, void* out, int32_t batch, int32_t h, int32_t wd,
-                     int32_t cin, int32_t cout, void* stream);
+/* direct 3x3 convs (pad 1) with a tiny channel count on one side (conv_in 4→C, conv_out C→4, VAE 3→128 / 128→3):
+ * w bf16 [cout, 9*cin] (tap-major).  cin <= 8: x per in_mode (0 NHWC bf16, 1 NCHW bf16, 2 NCHW fp32, 3 NCHW fp16),
+ * out NHWC bf16 (out_mode 0).  cout <= 8: x NHWC bf16 (in_mode 0), out per out_mode (0 NHWC bf16, 1 NCHW bf16,
+ * 2 NCHW fp32, 3 NCHW fp16).                                                                                */
+int fd_conv3x3_small(const void* x, int32_t in_mode, const void* w, const float* bias, void* out, int32_t out_mode,
+                     int64_t out_ld, int32_t batch, int32_t h, int32_t wd, int32_t cin, int32_t cout, void* stream);
+/* 1x1 conv with <= 8 channels on both sides, NCHW, dtype 0 bf16 / 1 fp16 / 2 fp32 (quant_conv / post_quant_conv,
+ * with the 1/scaling_factor latent scaling folded in as in_scale): out = W (in_scale * x) + b                  */
+int fd_conv1x1_small(const void* x, int32_t in_dtype, const float* w, const float* bias, void* out, int32_t out_dtype,
+                     int32_t batch, int32_t cin, int32_t cout, int64_t hw, float in_scale, void* stream);
 /* tiny-M linear: out[m, n] = act(sum_k x[m,k] w[n,k] + bias[n]); x fp32 [M,K], w bf16 [N,K], out fp32; act 0/1(SiLU)
  * (time / micro-conditioning embedding MLPs and the 17 time_emb_proj, …extension.py:543-564)               */
-int fd_linear_smallm(const float* x, const void* w, const float* bias, float* out, int32_t m, int32_t n, int32_t k,
-                     int32_t act_in_silu, int32_t act_out_silu, void* stream);
-/* sinusoidal timestep embedding (flip_sin_to_cos=True, shift 0): out[i, :] = [cos(v_i f), sin(v_i f)], fp32   */
-int fd_timestep_embedding(const float* values, float* out, int32_t n, int32_t dim, int64_t out_ld, void* stream);
+int fd_linear_smallm(const float* x, const void* w, const float* bias, const float* addend_or_null, float* out, int32_t m,
+                     int32_t n, int32_t k, int32_t act_in_silu, int32_t act_out_silu, void* stream);
+/* sinusoidal timestep embedding (flip_sin_to_cos=True, shift 0): row i = [cos(v_i f), sin(v_i f)], fp32, written
+ * at out + (i / inner) * outer_ld + (i % inner) * dim  (inner = 6, outer_ld = 2816 packs the SDXL time_ids).   */
+int fd_timestep_embedding(const float* values, float* out, int32_t n, int32_t dim, int32_t inner, int64_t outer_ld,
+                          void* stream);
 /* FaithDiff information-transformer attention across the BATCH axis (nn.MultiheadAttention with
- * batch_first=False fed (B, HW, E), …extension.py:242,576-577): qkv bf16 [B, HW, 3E] → out bf16 [B, HW, E]   */
-int fd_batch_axis_attention(const void* qkv, void* out, int32_t batch, int64_t hw, int32_t embed, int32_t heads,
-                            void* stream);
+ * batch_first=False fed (B, HW, E), …extension.py:242,576-577): qkv bf16 [G, L, HW, 3E] → out bf16 [G, L, HW, E];
+ * softmax over the L (= reference batch, <= 4) axis per pixel and head; G independent groups (batched tiles).  */
+int fd_batch_axis_attention(const void* qkv, void* out, int32_t groups, int32_t seq, int64_t hw, int32_t embed,
+                            int32_t heads, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tiled-latent kernels (pipeline_FaithDiff_tlc.py:101-252, :1324-1409)
@@ -124,13 +135,16 @@ int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, cons
                        const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1,
                        int32_t k2, float guidance, float sigma, float sigma_next, float next_scale_div,
                        float* canvas_f32, void* canvas_lowp, void* next_tiles, void* next_scaled, void* stream);
-/* accumulate-only variant for the multi-GPU path: adds this rank's tiles (weighted) into a zeroed fp32 canvas
- * (numerator only); after the all-reduce fd_canvas_finalize divides by the static count map.                 */
-int fd_tile_accumulate(const void* tiles, int32_t tile_dtype, const double* weights, const int32_t* origins_ij,
-                       int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num,
-                       void* stream);
+/* accumulate-only variant for the multi-GPU path: adds this rank's tiles (weighted; with eps != NULL the CFG +
+ * Euler update is applied first, as in fd_cfg_euler_blend) into an fp32 numerator canvas; after the NCCL
+ * all-reduce fd_canvas_finalize divides by the static count map (= this call on all-ones fp32 tiles).        */
+int fd_tile_accumulate(const void* tiles, const void* eps_or_null, int32_t dtype, const double* weights,
+                       const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2,
+                       float guidance, float sigma, float sigma_next, float* canvas_num, void* stream);
 int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
                        int32_t lowp_dtype, int64_t n, void* stream);
+/* EulerDiscreteScheduler.scale_model_input (pipeline…:1336): out = x / sqrt(sigma^2+1), rounded to dtype         */
+int fd_scale_div(const void* x, void* out, int32_t dtype, float div, int64_t n, void* stream);
 /* VAE / LQ-encoder seam blend (Encoder.blend_v/blend_h, …extension.py:150-162): in-place linear cross-fade of
  * the first `extent` rows (vertical=1) or columns of b with the last `extent` of a; NCHW, dtype 0/1/2.        */
 int fd_seam_blend(const void* a, void* b, int32_t dtype, int32_t c, int32_t ah, int32_t aw, int32_t bh, int32_t bw,

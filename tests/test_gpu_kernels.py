@@ -1,0 +1,172 @@
+"""-m gpu: kernel-level parity of the C-ABI kernels (called through ctypes) against torch fp32 on the same inputs.
+Tolerances: bf16 outputs → rel-L2 <= 5e-3 (one bf16 rounding of an fp32-accumulated result is ~2e-3)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def rel(a, b):
+    return ((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-20)).item()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from faithdiff_dev_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (154, 1280, 2048), (2048, 1280, 1280), (300, 320, 72), (2, 1280, 320)])
+def test_gemm_plain(ops, M, N, K):
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda").to(BF)
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF)
+    b = torch.randn(N, device="cuda")
+    out = ops.gemm(a, w, bias=b)
+    assert rel(out, a.float() @ w.float().t() + b) < 5e-3
+
+
+def test_gemm_epilogues(ops):
+    torch.manual_seed(1)
+    M, N, K = 1024, 640, 320
+    a = torch.randn(M, K, device="cuda").to(BF)
+    a2 = torch.randn(M, 128, device="cuda").to(BF)
+    w = (torch.randn(N, K + 128, device="cuda") / K ** 0.5).to(BF)
+    b = torch.randn(N, device="cuda")
+    r = torch.randn(M, N, device="cuda").to(BF)
+    rb = torch.randn(4, N, device="cuda")
+    ref = torch.cat([a, a2], 1).float() @ w.float().t() + b
+    assert rel(ops.gemm(a, w, a2=a2, bias=b, residual=r), ref + r.float()) < 5e-3
+    assert rel(ops.gemm(a, w, a2=a2, bias=b, act=1), F.silu(ref)) < 5e-3
+    assert rel(ops.gemm(a, w, a2=a2, bias=b, act=3), ref * torch.sigmoid(1.702 * ref)) < 5e-3
+    assert rel(ops.gemm(a, w, a2=a2, bias=b, rowbias=rb, rows_per_batch=M // 4), ref + rb.repeat_interleave(M // 4, 0)) < 5e-3
+    assert rel(ops.gemm(a, w, a2=a2, bias=b, act=2), ref[:, 0::2] * F.gelu(ref[:, 1::2])) < 5e-3
+    assert rel(ops.gemm(a, w, a2=a2, out_fp32=True), ref - b) < 1e-5
+    bm = torch.randn(M, device="cuda")
+    assert rel(ops.gemm(a, w, a2=a2, bias=bm, bias_along_m=True), ref - b + bm[:, None]) < 5e-3
+    # strided A view and strided output
+    big = torch.randn(M, 3 * K, device="cuda").to(BF)
+    wv = (torch.randn(N, K, device="cuda") / K ** 0.5).to(BF)
+    outbuf = torch.zeros(M, 2 * N, device="cuda", dtype=BF)
+    ops.gemm(big[:, K:2 * K], wv, out=outbuf[:, N:])
+    assert rel(outbuf[:, N:], big[:, K:2 * K].float() @ wv.float().t()) < 5e-3 and outbuf[:, :N].abs().max() == 0
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,N,stride,pad_lo", [
+    (2, 32, 32, 128, 0, 128, 1, 1), (2, 18, 14, 64, 0, 96, 1, 1), (2, 16, 16, 64, 128, 64, 1, 1), (1, 4, 4, 256, 256, 256, 1, 1),
+    (2, 32, 32, 320, 0, 320, 2, 1), (1, 64, 48, 128, 0, 128, 2, 0), (1, 9, 7, 64, 0, 64, 2, 1), (2, 128, 128, 320, 0, 320, 1, 1)])
+def test_conv3x3(ops, B, H, W, C0, C1, N, stride, pad_lo):
+    torch.manual_seed(2)
+    x = torch.randn(B, H, W, C0, device="cuda").to(BF)
+    x2 = torch.randn(B, H, W, C1, device="cuda").to(BF) if C1 else None
+    ct = C0 + C1
+    w = (torch.randn(N, ct, 3, 3, device="cuda") / (9 * ct) ** 0.5).to(BF)
+    b = torch.randn(N, device="cuda")
+    rb = torch.randn(B, N, device="cuda")
+    xin = torch.cat([x] + ([x2] if C1 else []), -1).permute(0, 3, 1, 2).float()
+    if stride == 1:
+        ref = F.conv2d(xin, w.float(), b, padding=1)
+    elif pad_lo:
+        ref = F.conv2d(xin, w.float(), b, stride=2, padding=1)
+    else:
+        ref = F.conv2d(F.pad(xin, (0, 1, 0, 1)), w.float(), b, stride=2)
+    ref = ref + rb[:, :, None, None]
+    wp = w.permute(0, 2, 3, 1).reshape(N, -1).contiguous()
+    out = ops.conv3x3(x, wp, x2=x2, bias=b, rowbias=rb, stride=stride, pad_lo=pad_lo)
+    assert out.shape == (B, ref.shape[2], ref.shape[3], N)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+
+
+@pytest.mark.parametrize("B,heads,lq,lk", [(2, 2, 256, 256), (2, 10, 4096, 4096), (2, 4, 1024, 77), (1, 1, 16, 16), (2, 3, 200, 333)])
+def test_attention_d64(ops, B, heads, lq, lk):
+    torch.manual_seed(3)
+    C = heads * 64
+    q = torch.randn(B * lq, C, device="cuda").to(BF)
+    kv = torch.randn(B * lk, 2 * C, device="cuda").to(BF)
+    out = ops.attention(q, kv[:, :C], kv[:, C:], B, heads, lq, lk, 0.125)
+    qq = q.float().view(B, lq, heads, 64).transpose(1, 2)
+    kk = kv[:, :C].float().reshape(B, lk, heads, 64).transpose(1, 2)
+    vv = kv[:, C:].float().reshape(B, lk, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * lq, C)
+    assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,HW,C0,C1,silu", [(2, 1024, 320, 0, True), (2, 256, 1280, 640, True), (1, 4096, 64, 0, False), (3, 100, 32, 32, True)])
+def test_groupnorm(ops, B, HW, C0, C1, silu):
+    torch.manual_seed(4)
+    x = (torch.randn(B, HW, 1, C0, device="cuda") * 2 + 0.5).to(BF)
+    x2 = torch.randn(B, HW, 1, C1, device="cuda").to(BF) if C1 else None
+    ct = C0 + C1
+    g, b = torch.randn(ct, device="cuda"), torch.randn(ct, device="cuda")
+    out = ops.groupnorm(x, g, b, 32, 1e-5, silu, x2=x2)
+    xin = torch.cat([x] + ([x2] if C1 else []), -1).float().permute(0, 3, 1, 2)
+    ref = F.group_norm(xin, 32, g, b, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(8192, 640), (2048, 1280), (100, 128)])
+def test_layernorm(ops, rows, cols):
+    torch.manual_seed(5)
+    x = (torch.randn(rows, cols, device="cuda") * 3 + 1).to(BF)
+    g, b = torch.randn(cols, device="cuda"), torch.randn(cols, device="cuda")
+    assert rel(ops.layernorm(x, g, b, 1e-5), F.layer_norm(x.float(), (cols,), g, b, 1e-5)) < 5e-3
+
+
+def test_small_convs_and_layouts(ops):
+    torch.manual_seed(6)
+    x = torch.randn(2, 4, 20, 28, device="cuda").to(BF)
+    w = (torch.randn(64, 4, 3, 3, device="cuda") / 6).to(BF)
+    b = torch.randn(64, device="cuda")
+    out = ops.conv3x3_small_in(x, w.permute(0, 2, 3, 1).reshape(64, -1).contiguous(), b)
+    assert rel(out.permute(0, 3, 1, 2), F.conv2d(x.float(), w.float(), b, padding=1)) < 5e-3
+    y = torch.randn(2, 20, 28, 64, device="cuda").to(BF)
+    w2 = (torch.randn(4, 64, 3, 3, device="cuda") / 24).to(BF)
+    b2 = torch.randn(4, device="cuda")
+    o2 = ops.conv3x3_small_out(y, w2.permute(0, 2, 3, 1).reshape(4, -1).contiguous(), b2, out_dtype=BF)
+    assert rel(o2, F.conv2d(y.permute(0, 3, 1, 2).float(), w2.float(), b2, padding=1)) < 5e-3
+    assert torch.equal(ops.nhwc_to_nchw(ops.nchw_to_nhwc(x)), x)
+    up = ops.upsample_nearest(y)
+    assert torch.equal(up.permute(0, 3, 1, 2), F.interpolate(y.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"))
+    up2 = ops.upsample_nearest(y, 37, 51)
+    assert torch.equal(up2.permute(0, 3, 1, 2), F.interpolate(y.permute(0, 3, 1, 2).float(), size=(37, 51), mode="nearest").to(BF))
+    z = torch.randn(1, 4, 9, 11, device="cuda")
+    wq, bq = torch.randn(4, 4, device="cuda"), torch.randn(4, device="cuda")
+    assert rel(ops.conv1x1_small(z, wq, bq, in_scale=0.5), torch.einsum("oc,bchw->bohw", wq.double(), z.double() * 0.5) + bq.double()[None, :, None, None]) < 1e-5
+
+
+def test_embeddings_and_small_linear(ops):
+    torch.manual_seed(7)
+    import math
+    t = torch.tensor([951.0, 1.0, 500.0], device="cuda")
+    e = ops.timestep_embedding(t, 320)
+    f = torch.exp(-math.log(10000) * torch.arange(160, dtype=torch.float32, device="cuda") / 160)
+    a = t[:, None] * f[None]
+    ref = torch.cat([torch.cos(a), torch.sin(a)], -1)
+    assert (e - ref).abs().max() < 2e-3      # args up to ~1e3 rad in fp32: a few ulp of the argument
+    x = torch.randn(2, 320, device="cuda")
+    w = (torch.randn(1280, 320, device="cuda") / 18).to(BF)
+    b = torch.randn(1280, device="cuda")
+    add = torch.randn(2, 1280, device="cuda")
+    out = ops.linear_smallm(x, w, b, addend=add, silu_in=True, silu_out=True)
+    assert rel(out, F.silu(F.silu(x) @ w.float().t() + b) + add) < 1e-4
+
+
+def test_batch_axis_attention(ops):
+    torch.manual_seed(8)
+    G, L, HW, E, heads = 2, 2, 300, 640, 8
+    qkv = torch.randn(G * L * HW, 3 * E, device="cuda").to(BF)
+    out = ops.batch_axis_attention(qkv, G, L, HW, E, heads)
+    x = qkv.float().view(G, L, HW, 3, heads, E // heads)
+    q, k, v = x[:, :, :, 0], x[:, :, :, 1], x[:, :, :, 2]          # [G, L, HW, heads, d]
+    s = torch.einsum("gapnd,gbpnd->gpnab", q, k) * (E // heads) ** -0.5
+    ref = torch.einsum("gpnab,gbpnd->gapnd", s.softmax(-1), v).reshape(G * L * HW, E)
+    assert rel(out, ref) < 5e-3
+
+
+def test_softmax_rows(ops):
+    s = torch.randn(300, 1000, device="cuda") * 5
+    assert rel(ops.softmax_rows(s, 0.3), (s * 0.3).softmax(-1)) < 5e-3
