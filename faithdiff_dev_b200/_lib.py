@@ -64,9 +64,14 @@ _SIGS = {
     "fd_adain_color_fix": [vp, vp, vp, i32, i32, vp, vp],
     "fd_wavelet_color_fix": [vp, vp, vp, i32, i32, vp, vp],
 }
-EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count"] + list(_SIGS)
+EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count", "fd_sizeof_gemm_desc"] + list(_SIGS)
 for _n, _a in _SIGS.items():
     getattr(lib, _n).argtypes = _a
+
+
+if lib.fd_sizeof_gemm_desc() != C.sizeof(GemmDesc):
+    raise ImportError("faithdiff_dev_b200: GemmDesc mirror (%d B) does not match fd_gemm_desc (%d B)"
+                      % (C.sizeof(GemmDesc), lib.fd_sizeof_gemm_desc()))
 
 
 def check(status, what):

@@ -98,16 +98,21 @@ class VaeAttention:
         L = H * Wd
         n = ops.groupnorm(x, self.ng, self.nb, self.groups, self.eps, False)
         out = torch.empty_like(x)
+        Lp = (L + 7) // 8 * 8            # token count padded to the 16-byte vector width of the GEMM epilogue
         for b in range(B):
             nb = n[b].reshape(L, Cc)
+            if Lp != L:
+                pad = torch.zeros((Lp, Cc), device=x.device, dtype=BF16)
+                pad[:L] = nb
+                nb = pad
             q = ops.gemm(nb, self.wq, bias=self.bq)
             k = ops.gemm(nb, self.wk, bias=self.bk)
-            vt = ops.gemm(self.wv, nb, bias=self.bv, bias_along_m=True)           # V^T [C, L] = Wv · X^T
-            s = ops.gemm(q, k, out_fp32=True)                                      # [L, L] fp32 scores
-            p = ops.softmax_rows(s, alpha=Cc ** -0.5)
+            vt = ops.gemm(self.wv, nb, bias=self.bv, bias_along_m=True)           # V^T [C, Lp] = Wv · X^T
+            s = ops.gemm(q, k, out_fp32=True)                                      # [Lp, Lp] fp32 scores
+            p = ops.softmax_rows(s, alpha=Cc ** -0.5, cols=L)                      # pad key columns get p = 0
             del s
-            o = ops.gemm(p, vt)                                                    # [L, C]
-            ops.gemm(o, self.wo, bias=self.bo, residual=x[b].reshape(L, Cc), out=out[b].reshape(L, Cc))
+            o = ops.gemm(p, vt)                                                    # [Lp, C]
+            ops.gemm(o[:L], self.wo, bias=self.bo, residual=x[b].reshape(L, Cc), out=out[b].reshape(L, Cc))
         return out
 
 

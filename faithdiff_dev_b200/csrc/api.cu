@@ -65,3 +65,4 @@ int encode_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64
 extern "C" const char* fd_last_error(void) { return fd::g_err; }
 extern "C" int fd_version(void) { return 100; }
 extern "C" int64_t fd_launch_count(void) { return fd::g_launches; }
+extern "C" int fd_sizeof_gemm_desc(void) { return (int)sizeof(fd_gemm_desc); }

@@ -98,10 +98,11 @@ def attention(q, k, v, batch, heads, lq, lk, scale, out=None):
     return out
 
 
-def softmax_rows(s, alpha=1.0):
-    p = torch.empty(s.shape, device=s.device, dtype=BF16)
-    check(lib.fd_softmax_rows(_p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], s.shape[1], alpha, _stream()),
-          "fd_softmax_rows")
+def softmax_rows(s, alpha=1.0, cols=None):
+    """Row softmax over the first `cols` columns (default all); remaining columns of p are zero."""
+    cols = cols or s.shape[1]
+    p = torch.empty(s.shape, device=s.device, dtype=BF16) if cols == s.shape[1] else torch.zeros(s.shape, device=s.device, dtype=BF16)
+    check(lib.fd_softmax_rows(_p(s), s.stride(0), _p(p), p.stride(0), s.shape[0], cols, alpha, _stream()), "fd_softmax_rows")
     return p
 
 

@@ -89,7 +89,7 @@ class UNet2DConditionModel:
         self.spatial_ch_projs = None
         self.agg_net = None
         self._loaded = False
-        self._kv_cache = (None, None)
+        self._kv_cache = (None, None, None)
         self.num_upsamplers = len(c.block_out_channels) - 1
 
     # ------------------------------------------------------------------ weights
@@ -192,7 +192,7 @@ class UNet2DConditionModel:
             if missing:
                 raise RuntimeError("unexpected keys in state_dict: %s…" % missing[:5])
         self._loaded = True
-        self._kv_cache = (None, None)
+        self._kv_cache = (None, None, None)
         return self
 
     # ------------------------------------------------------------------ pieces
@@ -223,16 +223,16 @@ class UNet2DConditionModel:
 
     def text_kv(self, encoder_hidden_states):
         """Cross-attention K/V of the text tokens for all 70 transformer blocks; identical for every tile and
-        step, so cached on the tensor identity."""
-        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version, tuple(encoder_hidden_states.shape))
-        if self._kv_cache[0] == key:
-            return self._kv_cache[1]
+        step, so cached on the tensor's identity + version counter."""
+        c = self._kv_cache
+        if c[0] is encoder_hidden_states and c[1] == encoder_hidden_states._version:
+            return c[2]                 # the cache holds a reference, so the tensor's storage cannot be recycled
         ehs = encoder_hidden_states.to(self.device, BF16).contiguous()
         B, lk, D = ehs.shape
         t2 = ehs.reshape(B * lk, D)
         kv = [[blk.text_kv(t2) for blk in tr.blocks] for tr in self._transformers]
-        self._kv_cache = (key, (kv, lk))
-        return self._kv_cache[1]
+        self._kv_cache = (encoder_hidden_states, encoder_hidden_states._version, (kv, lk))
+        return self._kv_cache[2]
 
     def condition_embed(self, lq_nhwc):
         """ControlNetConditioningEmbedding (…extension.py:213-219): step-invariant per tile."""

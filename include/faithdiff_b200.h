@@ -56,6 +56,7 @@ typedef struct fd_gemm_desc {
   int32_t block_n;       /* 0 = auto; else multiple of 32 in [32, 256]                                    */
 } fd_gemm_desc;
 int fd_gemm(const fd_gemm_desc* d, void* stream);
+int fd_sizeof_gemm_desc(void);   /* lets a foreign-language binding verify its struct mirror */
 
 /* ---------------------------------------------------------------------------------------------------------
  * Flash-style attention, head_dim 64, bf16, non-causal, no mask (tcgen05 QK^T and PV, online softmax in fp32).

@@ -1,0 +1,121 @@
+"""-m "not gpu": host-side logic of the product package (no kernel launches) and the C-ABI surface."""
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    import ctypes
+    from faithdiff_dev_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "faithdiff_b200.h")).read()
+    declared = set(re.findall(r"\b(fd_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 28
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert _lib.lib.fd_version() == 100 and _lib.lib.fd_launch_count() == 0
+    assert _lib.lib.fd_groupnorm_work_floats(2, 32, 320) > 0
+    # the ctypes GemmDesc mirrors the C struct size (catches field drift)
+    m = re.search(r"typedef struct fd_gemm_desc \{(.*?)\} fd_gemm_desc;", hdr, re.S)
+    assert m and ctypes.sizeof(_lib.GemmDesc) == lib.fd_sizeof_gemm_desc() == 176
+
+
+def test_no_cuda_no_fallback():
+    """The product path must fail loudly without a GPU — never compute on the CPU."""
+    import faithdiff_dev_b200 as fd
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    la = fd.LocalAttention((16, 16), 0.5)
+    with pytest.raises(RuntimeError):
+        la.grids(torch.zeros(1, 4, 32, 32))
+    enc = fd.Encoder()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 3, 64, 64))
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import faithdiff_dev_b200._lib as L; import os; "
+            "L.LIB_PATH = '/nonexistent.so'; \ntry:\n  L._load()\n  print('LOADED')\nexcept ImportError as e:\n  print('IMPORTERROR')") % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True).stdout
+    assert "IMPORTERROR" in out
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "faithdiff_dev_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no oracle", ""), fn
+
+
+def test_tile_layout_matches_golden(golden_dir):
+    from faithdiff_dev_b200.tiling import gaussian_weights, tile_origins
+    man = json.load(open(os.path.join(golden_dir, "manifest.json")))
+    for name, c in man["layout"].items():
+        idx, k1, k2 = tile_origins(c["h"], c["w"], c["k"], c["k"], c["overlap"])
+        assert [list(x) for x in idx] == c["idxes"] and (k1, k2) == (c["k1"], c["k2"]), name
+    assert np.array_equal(gaussian_weights(128, 128), np.load(os.path.join(golden_dir, "gaussian_weights_128.npy")))
+    assert np.array_equal(gaussian_weights(64, 64), np.load(os.path.join(golden_dir, "gaussian_weights_64.npy")))
+    # empty / degenerate: one tile when the canvas is smaller than the kernel
+    assert tile_origins(10, 12, 128, 128, 0.5) == ([(0, 0)], 10, 12)
+
+
+def test_scheduler_scalars_match_golden(golden_dir):
+    from faithdiff_dev_b200.scheduler import DDPMScheduler, EulerDiscreteScheduler
+    man = json.load(open(os.path.join(golden_dir, "manifest.json")))
+    s = EulerDiscreteScheduler()
+    s.set_timesteps(20)
+    assert s.timesteps.tolist() == man["euler20"]["timesteps"]
+    assert [float(v) for v in s.sigmas] == man["euler20"]["sigmas"]
+    assert float(s.init_noise_sigma) == man["euler20"]["init_noise_sigma"]
+    sig, nxt, div = s.step_scalars(0)
+    assert sig == man["euler20"]["sigmas"][0] and nxt == man["euler20"]["sigmas"][1]
+    assert div == float((torch.tensor(sig) ** 2 + 1) ** 0.5)
+    x0, n = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
+    d = DDPMScheduler()
+    a = d.alphas_cumprod[999]
+    assert torch.equal(d.add_noise(x0, n, torch.tensor([999])), a ** 0.5 * x0 + (1 - a) ** 0.5 * n)
+
+
+def test_weight_packing():
+    from faithdiff_dev_b200.blocks import Weights, interleave_geglu
+    w = torch.arange(2 * 3 * 9, dtype=torch.float32).reshape(2, 3, 3, 3)
+    W = Weights({"c.weight": w}, "cpu")
+    p = W.conv3("c.weight").float()
+    for o in range(2):
+        for r in range(3):
+            for s in range(3):
+                for c in range(3):
+                    assert p[o, (r * 3 + s) * 3 + c] == w[o, c, r, s]
+    ff = torch.arange(8 * 2, dtype=torch.float32).reshape(8, 2)
+    b = torch.arange(8, dtype=torch.float32)
+    wi, bi = interleave_geglu(ff, b)
+    assert torch.equal(wi[0::2], ff[:4]) and torch.equal(wi[1::2], ff[4:]) and torch.equal(bi, torch.tensor([0., 4, 1, 5, 2, 6, 3, 7]))
+
+
+def test_pipeline_input_validation():
+    import faithdiff_dev_b200 as fd
+
+    class V:
+        config = type("C", (), {"block_out_channels": (1, 2, 3, 4), "latent_channels": 4, "scaling_factor": 0.13025})()
+    class U:
+        config = type("C", (), {"sample_size": 128})()
+    pipe = fd.FaithDiffStableDiffusionXLPipeline(V(), None, None, None, None, None, U(), fd.EulerDiscreteScheduler(), fd.DDPMScheduler())
+    with pytest.raises(ValueError):
+        pipe.check_inputs(None, "x", 100, 128, None, None, None, None, None)       # not divisible by 8
+    with pytest.raises(ValueError):
+        pipe.check_inputs(None, None, 128, 128, None, None, None, None, None)      # neither prompt nor embeds
+    with pytest.raises(ValueError):
+        pipe.check_inputs(None, "x", 128, 128, torch.zeros(1), None, None, None, None)
+    with pytest.raises(ValueError):
+        pipe.check_inputs(None, None, 128, 128, torch.zeros(1), None, None, None, None)   # embeds without pooled
+    with pytest.raises(NotImplementedError):
+        pipe.enable_model_cpu_offload()
+    with pytest.raises(RuntimeError):
+        pipe.to("cpu")
+    assert pipe.vae_scale_factor == 8
