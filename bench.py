@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — FaithDiff tiled latent-denoising hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU cores
+
+Metric (BASELINE.json): output MP/s of a 20-step 2x super-resolution of a 1920x1080 synthetic LQ image to 3840x2160
+(28 overlapping 128x128 latent tiles, Gaussian blend each step, tiled LQ encoder, tiled VAE, AdaIN colour fix) with
+random-init weights of the SDXL + FaithDiff architecture.  One "step" = one whole restoration.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "output_megapixels_per_second"
+UNIT = "MP/s"
+# algorithmic FLOPs (2*MAC) of one reference tile-step (B=2 CFG pair, 128x128 latent): BASELINE.md §3
+TILE_STEP_TFLOP_128 = 14.216
+TILE_STEP_TFLOP_64 = 2 * (1.589 + 0.347 / 4)
+
+
+def workload(name):
+    if name == "4k":
+        return dict(name="cfg3: 1920x1080 -> 3840x2160 2x SR, 20 steps, 1024-px latent tiles overlap 0.5 (28 tiles), tiled LQ "
+                         "encoder + tiled VAE, start_point=lr, adain colour fix", lq=(1920, 1080), scale=2, steps=20)
+    if name == "1k":
+        return dict(name="cfg2: 512x512 -> 1024x1024 2x SR, 20 steps, 1 tile", lq=(512, 512), scale=2, steps=20)
+    if name == "tiny":
+        return dict(name="dev: 256x256 -> 512x512, 2 steps", lq=(256, 256), scale=2, steps=2)
+    raise SystemExit("unknown workload " + name)
+
+
+def synthetic_lq(w, h, seed=0):
+    """low-pass uniform noise RGB u8 (8x box down/up)."""
+    import numpy as np
+    from PIL import Image
+    rng = np.random.default_rng(seed)
+    small = rng.integers(0, 256, size=((h + 7) // 8, (w + 7) // 8, 3), dtype=np.uint8)
+    return Image.fromarray(small).resize((w, h), Image.BILINEAR)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]                     # upper half = samples under load
+            out.update(sm_mhz=sorted(busy)[len(busy) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def build_oracle_unet_fast():
+    """Oracle UNet (fp32, full SDXL + FaithDiff architecture) with weights drawn from one shared random buffer
+    (values are irrelevant for timing; avoids minutes of default-init RNG and 10 GB of unique weights)."""
+    import torch
+    from oracle import faithdiff_oracle as O
+    with torch.device("meta"):
+        u = O.FaithDiffUNet(**O.SDXL_UNET_CONFIG)
+        u.load_additional_layers(channel=512)
+    big = max(p.numel() for p in u.parameters())
+    base = (torch.rand(big, generator=torch.Generator().manual_seed(0)) * 2 - 1) * 0.02
+    u = u.to_empty(device="cpu")
+    for name, p in u.named_parameters():
+        if p.dim() > 1:
+            p.data = base[:p.numel()].view(p.shape)            # all matrices alias one buffer (read-only at inference)
+        elif ("norm" in name or "ln_" in name) and name.endswith("weight"):
+            p.data = torch.ones_like(p)
+        else:
+            p.data = torch.zeros_like(p)
+    return u.eval()
+
+
+def cpu_tile_step_seconds(latent, reps=1):
+    """Times the reference algorithm's tile-step (UNet forward with FaithDiff stem, CFG batch 2; restated in
+    oracle/faithdiff_oracle.py from unet_2d_condition_vae_extension.py:480-697) in fp32 on all host cores."""
+    import torch
+    torch.set_num_threads(os.cpu_count())
+    u = build_oracle_unet_fast()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, latent, latent, generator=g)
+    lq = torch.randn(2, 512, latent, latent, generator=g)
+    ehs = torch.randn(2, 77, 2048, generator=g)
+    te = torch.randn(2, 1280, generator=g)
+    ids = torch.tensor([[2160., 3840., 0., 0., 1024., 1024.]] * 2)
+
+    def once():
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            u(x, torch.tensor(951.), encoder_hidden_states=ehs, input_embedding=lq,
+              added_cond_kwargs={"text_embeds": te, "time_ids": ids}, return_dict=False)
+        return time.perf_counter() - t0
+    return once
+
+
+def reference_arm(args, wl):
+    """--impl reference: the reference's CPU implementation of the path (the oracle port — the real reference needs
+    diffusers, absent offline, and hard-codes 'cuda') on the box's host cores.  Each step = a bounded sample: ONE
+    tile-step at a 64x64 latent, scaled to the workload by algorithmic FLOPs."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    once = cpu_tile_step_seconds(64)
+    for _ in range(args.warmup):
+        once()
+    t = [once() for _ in range(args.steps)]
+    per = sum(t) / len(t)
+    W, H = wl["lq"][0] * wl["scale"], wl["lq"][1] * wl["scale"]
+    tiles = 28 if wl["lq"] == (1920, 1080) else 1
+    full = per * (TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64) * tiles * wl["steps"]
+    val = W * H / 1e6 / full
+    sample = ("1 UNet tile-step (CFG batch 2, 64x64 latent, fp32 torch on %d threads) = %.2f s; scaled by algorithmic FLOPs "
+              "x%.2f to a 128x128 tile and x%d tile-steps (LQ encoder / VAE / blend time not charged to the CPU)"
+              % (os.cpu_count(), per, TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64, tiles * wl["steps"]))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": wl["name"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def roofline_pass(pipe, torch, ops):
+    """Dominant kernel = gemm_tcgen05_kernel (all dense contractions).  One instrumented EAGER tile-step after the timed
+    region: every fd_gemm launch is bracketed by CUDA events on the launching stream while a long spin kernel keeps the
+    GPU behind the host (so event gaps are kernel time, not Python time)."""
+    import faithdiff_dev_b200.ops as O
+    g = [v for k, v in pipe._graphs.items() if k != "key"]
+    if not g:
+        return None
+    ts = max(g, key=lambda t: t.nb)
+    rec = []
+    orig_gemm, orig_conv = O.gemm, O.conv3x3
+
+    def gemm(a, w, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); r = orig_gemm(a, w, *args, **kw); e.record()
+        rec.append((s, e, 2.0 * a.shape[0] * w.shape[0] * w.shape[1]))
+        return r
+
+    def conv(x, w, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); r = orig_conv(x, w, *args, **kw); e.record()
+        rec.append((s, e, 2.0 * r.numel() * w.shape[1]))
+        return r
+    O.gemm, O.conv3x3 = gemm, conv
+    try:
+        torch.cuda._sleep(int(2e8))                # ~0.1 s head start for the host
+        ts._run()
+        torch.cuda.synchronize()
+    finally:
+        O.gemm, O.conv3x3 = orig_gemm, orig_conv
+    dur = sum(s.elapsed_time(e) for s, e, _ in rec) * 1e-3
+    flops = sum(f for _, _, f in rec)
+    return {"launches": len(rec), "seconds": dur, "flops": flops, "tiles": ts.nb}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="4k")
+    ap.add_argument("--tiles-per-launch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = workload(args.workload)
+    if args.impl == "reference":
+        return reference_arm(args, wl)
+
+    import numpy as np
+    import torch
+    from PIL import Image
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import faithdiff_dev_b200 as fd
+    from faithdiff_dev_b200 import arch, ops
+    from faithdiff_dev_b200.color_fix import color_fix_u8
+
+    unet = fd.UNet2DConditionModel(**arch.SDXL_UNET_CONFIG)
+    unet.load_state_dict(arch.random_state_dict(arch.unet_param_shapes(arch.SDXL_UNET_CONFIG), seed=1234))
+    vae = fd.AutoencoderKL(**arch.SDXL_VAE_CONFIG)
+    vae.load_state_dict(arch.random_state_dict(arch.vae_param_shapes(), seed=4321))
+    pipe = fd.FaithDiffStableDiffusionXLPipeline(vae, unet.denoise_encoder, None, None, None, None, unet,
+                                                 fd.EulerDiscreteScheduler(), fd.DDPMScheduler())
+    pipe.set_encoder_tile_settings()
+    pipe.enable_vae_tiling()
+    pipe.tiles_per_launch = args.tiles_per_launch
+    if world > 1:
+        pipe.set_distributed(rank, world)
+
+    # synthetic input exactly as test_wo_llava.py:78-82 prepares it: LANCZOS upscale of the LQ image, pad to x8
+    lq = synthetic_lq(*wl["lq"])
+    W, H = wl["lq"][0] * wl["scale"], wl["lq"][1] * wl["scale"]
+    up = lq.resize((W, H), Image.LANCZOS)
+    assert W % 8 == 0 and H % 8 == 0
+    host_u8 = torch.from_numpy(np.ascontiguousarray(np.asarray(up, dtype=np.uint8))).pin_memory()
+    dev_u8 = host_u8.cuda()
+    host_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
+    g = torch.Generator().manual_seed(7)
+    pe, npe = torch.randn(1, 77, 2048, generator=g).cuda(), torch.randn(1, 77, 2048, generator=g).cuda()
+    pp, npp = torch.randn(1, 1280, generator=g).cuda(), torch.randn(1, 1280, generator=g).cuda()
+    mp = W * H / 1e6
+
+    def restore(img, seed=42):
+        torch.manual_seed(seed)
+        out = pipe(lr_img=img, prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pp,
+                   negative_pooled_prompt_embeds=npp, num_inference_steps=wl["steps"], start_point="lr", height=H, width=W,
+                   overlap=0.5, guidance_scale=5.0, target_size=(1024, 1024),
+                   generator=torch.Generator(device="cuda").manual_seed(seed), output_type="u8").images[0]
+        return out
+
+    def step_device():                       # inputs already resident in HBM
+        return color_fix_u8(restore(dev_u8), dev_u8, "adain")
+
+    def step_host():                         # the call a user makes: host image in, host image out
+        out = restore(host_u8)               # H2D of the pinned u8 image happens inside (pipeline._preprocess)
+        fixed = color_fix_u8(out, pipe._last_input_u8, "adain")
+        host_out.copy_(fixed, non_blocking=True)
+        return fixed
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0, r0 = ops.launch_count(), pipe.graph_kernel_launches()
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        launches = (ops.launch_count() - n0) + (pipe.graph_kernel_launches() - r0)
+        return ms.item(), launches
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, launches = timed(step_device, args.steps)
+    stage = pipe.stage_times_ms()
+    clk = clocks.stop() if rank == 0 else {}
+    ms_e2e, _ = timed(step_host, args.steps)
+    value, e2e = args.steps * mp / (ms * 1e-3), args.steps * mp / (ms_e2e * 1e-3)
+
+    roof = None
+    cpu = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak, which = (peaks["bf16_tflops_sustained"], "measured (sustained cuBLAS bf16, MEASURED_PEAKS.json)") if \
+            "bf16_tflops_sustained" in peaks else (1400.0, "fallback (B200_PROFILING.md sustained)")
+        r = roofline_pass(pipe, torch, ops)
+        if r:
+            ach = r["flops"] / r["seconds"] / 1e12
+            roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "how": "executed FLOPs of all %d fd_gemm launches of one %d-tile UNet evaluation / their summed CUDA-event "
+                           "durations (instrumented eager pass after the timed region)" % (r["launches"], r["tiles"]),
+                    "avg_launch_us": r["seconds"] / r["launches"] * 1e6,
+                    "unet_tile_step_ms": stage["denoise"] / wl["steps"] / max(1, len(pipe.tlc_vae_latents.idxes)) * world,
+                    "path_tflops_vs_reference_algorithm": TILE_STEP_TFLOP_128 * len(pipe.tlc_vae_latents.idxes) * wl["steps"]
+                    / (stage["denoise"] * 1e-3) / world}
+        if world == 1 and not args.no_cpu_baseline:
+            once = cpu_tile_step_seconds(64)
+            once()
+            t = once()
+            tiles = len(pipe.tlc_vae_latents.idxes)
+            full = t * (TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64) * tiles * wl["steps"]
+            cpu = {"value": mp / full, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": "1 UNet tile-step (CFG batch 2, 64x64 latent, fp32 oracle on %d threads) = %.2f s, scaled by "
+                             "algorithmic FLOPs x%.2f and x%d tile-steps; encoder/VAE/blend not charged"
+                             % (os.cpu_count(), t, TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64, tiles * wl["steps"])}
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "tiles": len(pipe.tlc_vae_latents.idxes), "tiles_per_launch": args.tiles_per_launch,
+                       "parallelism": "tiles sharded round-robin over %d GPU(s), one NCCL all-reduce of the fp32 canvas per step" % world,
+                       "l2": "no explicit flush: each step streams 5.3 GB of weights 280x plus activations (>> 126 MB L2)",
+                       "stage_ms_last_step": {k: round(v, 1) for k, v in stage.items()}},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(host_out.numel()),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

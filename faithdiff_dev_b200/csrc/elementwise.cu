@@ -78,12 +78,18 @@ __device__ __forceinline__ float load_in(const void* x, int in_mode, long long b
   if (in_mode == 2) return reinterpret_cast<const float*>(x)[idx];
   return __half2float(reinterpret_cast<const __half*>(x)[idx]);
 }
+// weights staged TRANSPOSED in smem ([9*CIN][cout] fp32) so that the 8-cout slices read by consecutive threads are
+// consecutive 32-byte chunks (conflict-free); inputs live in registers (CIN is a compile-time constant).
+template <int CIN>
 __global__ void conv3x3_smallcin_kernel(const void* __restrict__ x, int in_mode, const __nv_bfloat16* __restrict__ w,
                                         const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, long long out_ld,
-                                        int batch, int h, int wd, int cin, int cout) {
-  extern __shared__ float sw[];   // [cout][9*cin]
-  const int kk = 9 * cin;
-  for (int i = threadIdx.x; i < cout * kk; i += blockDim.x) sw[i] = __bfloat162float(w[i]);
+                                        int batch, int h, int wd, int cout) {
+  extern __shared__ float sw[];   // [9*CIN][cout]
+  constexpr int KK = 9 * CIN;
+  for (int i = threadIdx.x; i < cout * KK; i += blockDim.x) {
+    const int oc = i / KK, k = i - oc * KK;
+    sw[k * cout + oc] = __bfloat162float(w[i]);
+  }
   __syncthreads();
   const int ng = cout >> 3;
   const long long total = (long long)batch * h * wd * ng;
@@ -93,23 +99,23 @@ __global__ void conv3x3_smallcin_kernel(const void* __restrict__ x, int in_mode,
     const int xx = (int)(t % wd); t /= wd;
     const int y = (int)(t % h);
     const long long b = t / h;
-    float in[72];
+    float in[KK];
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
       const int yy = y + tap / 3 - 1, xq = xx + tap % 3 - 1;
       const bool ok = yy >= 0 && yy < h && xq >= 0 && xq < wd;
-      for (int c = 0; c < cin; ++c) in[tap * 8 + c] = ok ? load_in(x, in_mode, b, c, yy, xq, cin, h, wd) : 0.f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) in[tap * CIN + c] = ok ? load_in(x, in_mode, b, c, yy, xq, CIN, h, wd) : 0.f;
     }
     float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int oc = g * 8 + j;
-      float acc = bias ? bias[oc] : 0.f;
-      const float* wr = sw + oc * kk;
+    for (int j = 0; j < 8; ++j) o[j] = bias ? bias[g * 8 + j] : 0.f;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
-        for (int c = 0; c < cin; ++c) acc += in[tap * 8 + c] * wr[tap * cin + c];
-      o[j] = acc;
+    for (int k = 0; k < KK; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + k * cout + g * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + k * cout + g * 8 + 4);
+      o[0] += in[k] * w0.x; o[1] += in[k] * w0.y; o[2] += in[k] * w0.z; o[3] += in[k] * w0.w;
+      o[4] += in[k] * w1.x; o[5] += in[k] * w1.y; o[6] += in[k] * w1.z; o[7] += in[k] * w1.w;
     }
     uint4 u;
     u.x = pack_bf16(o[0], o[1]); u.y = pack_bf16(o[2], o[3]); u.z = pack_bf16(o[4], o[5]); u.w = pack_bf16(o[6], o[7]);
@@ -429,11 +435,17 @@ extern "C" int fd_conv3x3_small(const void* x, int32_t in_mode, const void* w, c
     FD_REQUIRE(out_ld % 8 == 0 && ((uintptr_t)out % 16) == 0, "fd_conv3x3_small: output pitch/alignment");
     const size_t smem = (size_t)cout * 9 * cin * sizeof(float);
     FD_REQUIRE(smem <= 96 * 1024, "fd_conv3x3_small: weights too large for smem");
-    static bool attr = false;
-    if (!attr) { FD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    FD_REQUIRE(cin == 3 || cin == 4 || cin == 8, "fd_conv3x3_small: small-cin path supports cin 3, 4 or 8 (got %d)", cin);
     const long long total = (long long)batch * h * wd * (cout / 8);
-    conv3x3_smallcin_kernel<<<grid_for(total, 256, 8), 256, smem, stream>>>(x, in_mode, (const __nv_bfloat16*)w, bias,
-                                                                          (__nv_bfloat16*)out, out_ld, batch, h, wd, cin, cout);
+    const unsigned grid = grid_for(total, 256, 8);
+#define FD_LAUNCH_SMALLCIN(C)                                                                                              \
+    {                                                                                                                      \
+      static bool attr = false;                                                                                            \
+      if (!attr) { FD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_smallcin_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; } \
+      conv3x3_smallcin_kernel<C><<<grid, 256, smem, stream>>>(x, in_mode, (const __nv_bfloat16*)w, bias, (__nv_bfloat16*)out, out_ld, batch, h, wd, cout); \
+    }
+    if (cin == 3) FD_LAUNCH_SMALLCIN(3) else if (cin == 4) FD_LAUNCH_SMALLCIN(4) else FD_LAUNCH_SMALLCIN(8)
+#undef FD_LAUNCH_SMALLCIN
   } else {
     FD_REQUIRE(cout <= 8 && cin % 8 == 0 && in_mode == 0, "fd_conv3x3_small: small-cout path needs cout<=8, cin%%8==0, NHWC bf16 input");
     const size_t smem = (size_t)cout * 9 * cin * sizeof(__nv_bfloat16);

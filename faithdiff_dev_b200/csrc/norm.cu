@@ -67,26 +67,34 @@ __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, int c0, 
   }
 }
 
-// grid B; block 256
+// grid B; block 1024 (one warp per group: lanes stride over the chunk partials, fp64 warp-shuffle combine)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunks, int groups, int ct, long long hw,
                                    float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.x;
   const int cpg = ct / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int g = warp; g < groups; g += nwarps) {
     double s = 0.0, q = 0.0;
-    for (int c = 0; c < nchunks; ++c) {
-      const float* pp = partial + (((long long)b * nchunks + c) * groups + g) * 2;
-      s += (double)pp[0];
-      q += (double)pp[1];
+    for (int c = lane; c < nchunks; c += 32) {
+      const float2 pp = *reinterpret_cast<const float2*>(partial + (((long long)b * nchunks + c) * groups + g) * 2);
+      s += (double)pp.x;
+      q += (double)pp.y;
     }
-    const double n = (double)hw * cpg;
-    const double mean = s / n;
-    double var = q / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[g] = (float)mean;
-    s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane == 0) {
+      const double n = (double)hw * cpg;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < ct; c += blockDim.x) {
@@ -201,7 +209,7 @@ extern "C" int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int
   FD_REQUIRE(smem <= 48 * 1024, "fd_groupnorm_nhwc: smem %zu too large", smem);
   gn_partial_kernel<<<dim3(nchunks, batch), V * R, smem, stream>>>((const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1,
                                                                     c1, hw, groups, R, partial);
-  gn_finalize_kernel<<<batch, 256, 0, stream>>>(partial, nchunks, groups, ct, hw, eps, gamma, beta, scale, shift);
+  gn_finalize_kernel<<<batch, 1024, 0, stream>>>(partial, nchunks, groups, ct, hw, eps, gamma, beta, scale, shift);
   const long long total_vec = (long long)batch * hw * V;
   long long blocks = (total_vec + 255) / 256;
   const long long cap = (long long)num_sms() * 16;

@@ -221,6 +221,26 @@ class UNet2DConditionModel:
         emb = ops.linear_smallm(a, *self.ae2, addend=emb)
         return ops.linear_smallm(emb, self.temb_w, self.temb_b, silu_in=True)
 
+    def time_embedding_table(self, timesteps, text_embeds, time_ids):
+        """All per-resnet time biases of an image at once: timesteps [S], text_embeds [P,·] (P = CFG branches),
+        time_ids [T,6] (one row per tile) → fp32 [S, T, P, ΣC_out].  Same arithmetic as time_embeddings()."""
+        c = self.config
+        dev = self.device
+        S, T, P = timesteps.numel(), time_ids.shape[0], text_embeds.shape[0]
+        t = timesteps.to(dev, torch.float32).reshape(-1).contiguous()
+        e = ops.linear_smallm(ops.timestep_embedding(t, c.block_out_channels[0]), *self.te1, silu_out=True)
+        t_emb = ops.linear_smallm(e, *self.te2)                                       # [S, D]
+        ids = time_ids.to(dev).to(torch.float32).contiguous()
+        tdim = text_embeds.shape[-1]
+        add_in = torch.empty((T, P, self.ae1[0].shape[1]), device=dev, dtype=torch.float32)
+        add_in[:, :, :tdim] = text_embeds.to(dev, torch.float32)[None]
+        sin = ops.timestep_embedding(ids.reshape(-1), c.addition_time_embed_dim).reshape(T, 1, -1)
+        add_in[:, :, tdim:] = sin
+        a = ops.linear_smallm(add_in.reshape(T * P, -1), *self.ae1, silu_out=True)
+        aug = ops.linear_smallm(a, *self.ae2)                                         # [T*P, D]
+        emb = (t_emb[:, None, :] + aug[None, :, :]).reshape(S * T * P, -1).contiguous()
+        return ops.linear_smallm(emb, self.temb_w, self.temb_b, silu_in=True).reshape(S, T, P, -1)
+
     def text_kv(self, encoder_hidden_states):
         """Cross-attention K/V of the text tokens for all 70 transformer blocks; identical for every tile and
         step, so cached on the tensor's identity + version counter."""

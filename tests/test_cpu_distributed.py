@@ -1,0 +1,67 @@
+"""-m "not gpu": the N>1 host logic on CPU with gloo, world_size 2: tile sharding + per-step canvas exchange reproduce
+the single-process Gaussian blend (oracle arithmetic) up to fp32 summation order."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.distributed.init_process_group("gloo", rank=rank, world_size=world)
+    from faithdiff_dev_b200.dist import exchange_canvas, shard_tiles
+    from faithdiff_dev_b200.tiling import gaussian_weights, tile_origins
+    h, w, k = 40, 56, 16
+    idx, k1, k2 = tile_origins(h, w, k, k, 0.5)
+    wts = torch.from_numpy(gaussian_weights(k2, k1))
+    g = torch.Generator().manual_seed(3)
+    tiles = torch.randn(len(idx), 4, k1, k2, generator=g).to(torch.bfloat16)      # same on every rank
+    num = torch.zeros(1, 4, h, w)
+    cnt = torch.zeros(1, 4, h, w)
+    for t in shard_tiles(len(idx), rank, world):
+        i, j = idx[t]
+        num[0, :, i:i + k1, j:j + k2] += tiles[t] * wts
+    for (i, j) in idx:
+        cnt[0, :, i:i + k1, j:j + k2] += wts
+    exchange_canvas(num)
+    q.put((rank, (num / cnt)))
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_canvas_exchange_matches_single_process_blend():
+    from oracle import faithdiff_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    lo = O.LocalAttention((16, 16), 0.5)
+    lo.grids(torch.zeros(1, 4, 40, 56))
+    g = torch.Generator().manual_seed(3)
+    tiles = torch.randn(len(lo.idxes), 4, 16, 16, generator=g).to(torch.bfloat16)
+    ref = lo.grids_inverse(tiles)
+    assert torch.equal(res[0], res[1])                       # all ranks hold the same canvas after the exchange
+    assert (res[0] - ref).abs().max() <= 2e-6 * ref.abs().max()
+
+
+def test_shard_and_launch_plan():
+    from faithdiff_dev_b200.dist import plan_launch_groups, shard_tiles
+    for T, W in [(28, 1), (28, 2), (28, 4), (28, 8), (112, 8), (1, 8), (9, 4)]:
+        shards = [shard_tiles(T, r, W) for r in range(W)]
+        assert sorted(t for s in shards for t in s) == list(range(T))
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+    assert plan_launch_groups([0, 4, 8, 12, 16, 20, 24], [2, 1]) == [[0, 4], [8, 12], [16, 20], [24]]
+    assert plan_launch_groups([], [2, 1]) == []
+    assert plan_launch_groups([5], [2]) == [[5]]

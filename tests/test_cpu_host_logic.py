@@ -119,3 +119,28 @@ def test_pipeline_input_validation():
     with pytest.raises(RuntimeError):
         pipe.to("cpu")
     assert pipe.vae_scale_factor == 8
+
+
+def test_arch_key_layout_matches_oracle_and_known_counts():
+    """The product's own checkpoint key layout equals the oracle's state dicts (which equal the reference's, see
+    oracle/make_golden.py) and the public SDXL parameter totals."""
+    import math
+    from faithdiff_dev_b200 import arch
+    from oracle import faithdiff_oracle as O
+    with torch.device("meta"):
+        u = O.FaithDiffUNet(**O.SDXL_UNET_CONFIG)
+        u.load_additional_layers(channel=512)
+        v = O.AutoencoderKL()
+        ut = O.build_unet.__wrapped__ if hasattr(O.build_unet, "__wrapped__") else None
+    shapes = arch.unet_param_shapes(arch.SDXL_UNET_CONFIG)
+    ref = {k: tuple(p.shape) for k, p in u.state_dict().items()}
+    assert shapes == ref
+    assert sum(math.prod(s) for s in shapes.values()) == 2612197892
+    vs = arch.vae_param_shapes()
+    assert vs == {k: tuple(p.shape) for k, p in v.state_dict().items()}
+    assert sum(math.prod(s) for s in vs.values()) == 83653863
+    with torch.device("meta"):
+        t = O.FaithDiffUNet(**O.TINY_UNET_CONFIG)
+        t.load_additional_layers(channel=64, encoder_kwargs=O.TINY_ENCODER_CONFIG)
+    assert arch.unet_param_shapes(O.TINY_UNET_CONFIG, lq_channels=64, encoder_channels=(32, 64, 64, 64)) == \
+        {k: tuple(p.shape) for k, p in t.state_dict().items()}
