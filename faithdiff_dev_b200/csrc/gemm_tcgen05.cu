@@ -6,6 +6,10 @@
 // A operand is either a row-major matrix (2-D tensor map) or an NHWC image read through 4-D tensor maps with the
 // 3x3 filter taps expressed as shifted TMA boxes (out-of-bounds = zero fill = the conv's zero padding);
 // stride-2 convs use four phase-subsampled tensor maps of the same image (no data rearrangement).
+// Thread-block clusters (CM x CN CTAs, up to 2x2) share operand tiles through TMA multicast: the CN CTAs of one tile
+// row each fetch 1/CN of the A tile and multicast it to the row, the CM CTAs of one tile column each fetch 1/CM of the B
+// tile — per-SM L2->SMEM traffic per k-block drops from 16K+N*128 B to 16K/CN + N*128/CM B, which is what bounds a
+// 1-CTA tile (64 B/clk/SM from L2 feeds only ~55% of the tensor pipe at 128x160).
 #include "common.cuh"
 #include "../../include/faithdiff_b200.h"
 
@@ -20,7 +24,10 @@ struct GemmKParams {
   int m_tiles, n_tiles, block_n, stages;
   int taps, kb_per_tap, kb_src0, ctot, two_src;
   int tap_map[9], tap_dy[9], tap_dx[9];
-  int out_h, out_w, bw, bh, tiles_x, tiles_per_img;
+  int out_h, out_w, bw, bh, tiles_x, tiles_per_img, batch;
+  int cm, cn, m_super, n_super;      // cluster shape and super-tile grid
+  int pair;                          // 1: CTA pair (cta_group::2, UMMA M=256); cm = 2, cn = 1, B tile split across the pair
+  int a_part_dy, a_part_dx;          // conv: pixel offset of A part j inside the tile patch (split along y or x)
   // epilogue
   const float* bias;
   const float* rowbias;
@@ -38,7 +45,7 @@ constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;   // 16 KB
 constexpr int kAccCols = 256;                        // TMEM columns per accumulator stage
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
 struct __align__(8) PipeBarriers {
   uint64_t full[kMaxStages];
@@ -48,59 +55,90 @@ struct __align__(8) PipeBarriers {
   uint32_t tmem_base;
 };
 
+// kPair = true instantiates the cta_group::2 (CTA-pair, UMMA M=256) variant; a kernel containing cta_group::2
+// instructions can only be launched with an even cluster size, hence two instantiations.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int b_tile_bytes = p.block_n * kBlockK * 2;
+  const int b_tile_bytes = (kPair ? p.block_n / 2 : p.block_n) * kBlockK * 2;   // pair: each CTA holds half of B
   const int stage_bytes = kATileBytes + b_tile_bytes;
   PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)p.stages * stage_bytes);
+
+  const int csize = p.cm * p.cn;
+  uint32_t crank = 0;
+  if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int ci = crank % p.cm, cj = crank / p.cm;          // position of this CTA inside the cluster (m, n); pair: ci = rank
+  uint16_t amask = 0, bmask = 0;                              // CTAs sharing my A tile (same ci) / my B tile (same cj)
+  for (int j = 0; j < p.cn; ++j) amask |= (uint16_t)(1u << (ci + j * p.cm));
+  for (int i = 0; i < p.cm; ++i) bmask |= (uint16_t)(1u << (i + cj * p.cm));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.bmap);
     tma_prefetch_desc(&p.amap[0]);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], 1);
+      mbar_init(&bars->empty[s], kPair ? 1 : p.cm + p.cn - 1);   // every CTA that multicasts into this stage must see it freed
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 4);
+      mbar_init(&bars->tmem_empty[a], kPair ? 16 : 8);    // 8 epilogue warps (pair: leader collects both CTAs')
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, 512);
-    tmem_relinquish();
+    if constexpr (kPair) { tmem_alloc2(&bars->tmem_base, 512); tmem_relinquish2(); }
+    else { tmem_alloc(&bars->tmem_base, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (csize > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int num_super = p.m_super * p.n_super;
+  const int num_clusters = gridDim.x / csize;
+  const int cluster_id = blockIdx.x / csize;
   const int num_kb = p.taps * p.kb_per_tap;
+  const int a_part_bytes = kATileBytes / p.cn, b_part_bytes = kPair ? b_tile_bytes : b_tile_bytes / p.cm;
 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.m_tiles;
-        const int n_blk = tile / p.m_tiles;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
+        const int m_blk = (st % p.m_super) * p.cm + ci;
+        const int n_blk = (st / p.m_super) * p.cn + cj;
         int img = 0, y0 = 0, x0 = 0;
         if (p.mode != 0) {
           img = m_blk / p.tiles_per_img;
           const int r = m_blk - img * p.tiles_per_img;
-          y0 = (r / p.tiles_x) * p.bh;
-          x0 = (r % p.tiles_x) * p.bw;
+          y0 = (r / p.tiles_x) * p.bh + cj * p.a_part_dy;     // my 1/CN part of the A patch
+          x0 = (r % p.tiles_x) * p.bw + cj * p.a_part_dx;
         }
         for (int tap = 0; tap < p.taps; ++tap) {
           for (int kb = 0; kb < p.kb_per_tap; ++kb) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
             uint8_t* sa = smem + (size_t)stage * stage_bytes;
             uint8_t* sb = sa + kATileBytes;
+            if constexpr (kPair) {
+              // both CTAs' bytes complete on the leader's barrier; only the leader arms it
+              const uint32_t lead_bar = mapa_u32(smem_u32(&bars->full[stage]), 0);
+              if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2u * (uint32_t)stage_bytes);
+              const int c0p = kb * kBlockK;
+              const int kcolp = tap * p.ctot + kb * kBlockK;
+              if (p.mode == 0)
+                tma_load_2d_cg2(&p.amap[p.two_src ? (kb >= p.kb_src0) : 0], lead_bar, sa,
+                                p.two_src && kb >= p.kb_src0 ? (kb - p.kb_src0) * kBlockK : c0p, m_blk * kBlockM);
+              else
+                tma_load_4d_cg2(&p.amap[p.two_src ? (kb >= p.kb_src0) : p.tap_map[tap]], lead_bar, sa,
+                                p.two_src && kb >= p.kb_src0 ? (kb - p.kb_src0) * kBlockK : c0p, x0 + p.tap_dx[tap],
+                                y0 + p.tap_dy[tap], img);
+              tma_load_2d_cg2(&p.bmap, lead_bar, sb, kcolp, n_blk * p.block_n + (int)crank * (p.block_n / 2));
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+              continue;
+            }
             mbar_arrive_expect_tx(&bars->full[stage], (uint32_t)stage_bytes);
             int src, c0;
             if (p.two_src) {
@@ -110,25 +148,39 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
               src = p.tap_map[tap];
               c0 = kb * kBlockK;
             }
-            if (p.mode == 0)
-              tma_load_2d(&p.amap[src], &bars->full[stage], sa, c0, m_blk * kBlockM);
+            if (p.cn == 1) {
+              if (p.mode == 0)
+                tma_load_2d(&p.amap[src], &bars->full[stage], sa, c0, m_blk * kBlockM);
+              else
+                tma_load_4d(&p.amap[src], &bars->full[stage], sa, c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], img);
+            } else {
+              uint8_t* dst = sa + cj * a_part_bytes;
+              if (p.mode == 0)
+                tma_load_2d_mc(&p.amap[src], &bars->full[stage], dst, c0, m_blk * kBlockM + cj * (kBlockM / p.cn), amask);
+              else
+                tma_load_4d_mc(&p.amap[src], &bars->full[stage], dst, c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], img, amask);
+            }
+            const int kcol = tap * p.ctot + kb * kBlockK;
+            if (p.cm == 1)
+              tma_load_2d(&p.bmap, &bars->full[stage], sb, kcol, n_blk * p.block_n);
             else
-              tma_load_4d(&p.amap[src], &bars->full[stage], sa, c0, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], img);
-            tma_load_2d(&p.bmap, &bars->full[stage], sb, tap * p.ctot + kb * kBlockK, n_blk * p.block_n);
+              tma_load_2d_mc(&p.bmap, &bars->full[stage], sb + ci * b_part_bytes, kcol,
+                             n_blk * p.block_n + ci * (p.block_n / p.cm), bmask);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer (single thread)
-      const uint32_t idesc = umma_idesc(kBlockM, p.block_n, /*bf16*/ 1, 0, 0);
+    if (lane == 0 && !(kPair && crank != 0)) {
+      // ------------------------------------------------------------------ MMA issuer (single thread; pair: leader CTA only)
+      const uint32_t idesc = umma_idesc(kPair ? 2 * kBlockM : kBlockM, p.block_n, /*bf16*/ 1, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint16_t cmask = amask | bmask;
+      for (int st = cluster_id; st < num_super; st += num_clusters) {
         mbar_wait(&bars->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccCols;
@@ -141,24 +193,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           for (int k = 0; k < kBlockK / 16; ++k) {
             const uint64_t adesc = umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t bdesc = umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            if constexpr (kPair) umma_f16_cg2(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
+            else umma_f16(d_tmem, adesc, bdesc, idesc, (kb | k) != 0);
           }
-          tc_commit(&bars->empty[stage]);          // frees this smem stage once the MMAs above retire
+          // frees this smem stage (in every CTA that multicasts into it / in both CTAs of a pair) once the MMAs above retire
+          if constexpr (kPair) tc_commit_cg2_mc(&bars->empty[stage], 3);
+          else { if (csize == 1) tc_commit(&bars->empty[stage]); else tc_commit_mc(&bars->empty[stage], cmask); }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&bars->tmem_full[acc]);          // accumulator complete -> epilogue
+        if constexpr (kPair) tc_commit_cg2_mc(&bars->tmem_full[acc], 3);   // accumulator complete -> both CTAs' epilogues
+        else tc_commit(&bars->tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // -------------------------------------------------------------------- epilogue warps (2..5)
+    // -------------------------------------------------------------------- epilogue warps (2..9)
     const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
+    const int chalf = (warp - 2) >> 2;              // the two warps of a quadrant alternate 32-column chunks
     const int row_in_tile = quad * 32 + lane;
+    const int nchunks = p.block_n >> 5;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.m_tiles;
-      const int n_blk = tile / p.m_tiles;
+    for (int st = cluster_id; st < num_super; st += num_clusters) {
+      const int m_blk = (st % p.m_super) * p.cm + ci;
+      const int n_blk = (st / p.m_super) * p.cn + cj;
       long long row;
       bool valid;
       int sample;
@@ -171,20 +229,37 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         const int r = m_blk - img * p.tiles_per_img;
         const int y = (r / p.tiles_x) * p.bh + row_in_tile / p.bw;
         const int x = (r % p.tiles_x) * p.bw + row_in_tile % p.bw;
-        valid = (y < p.out_h) && (x < p.out_w);
+        valid = (img < p.batch) && (y < p.out_h) && (x < p.out_w);
         row = ((long long)img * p.out_h + y) * p.out_w + x;
         sample = img;
+      }
+      const int ncol0 = n_blk * p.block_n;
+      // residual rows are prefetched two 32-column chunks ahead (first two before the accumulator is even ready):
+      // each thread owns one output row, so these are long-latency L2 reads that must not sit on the critical path
+      const __nv_bfloat16* res_row = (p.residual && valid) ? p.residual + row * p.ld_res : nullptr;
+      uint4 r0[4], r1[4];
+      auto load_res = [&](int c, uint4 (&dst)[4]) {
+#pragma unroll
+        for (int g8 = 0; g8 < 4; ++g8) {
+          const int n = ncol0 + c * 32 + g8 * 8;
+          dst[g8] = (res_row && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + n)) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      };
+      if (p.residual) {
+        if (chalf < nchunks) load_res(chalf, r0);
+        if (chalf + 2 < nchunks) load_res(chalf + 2, r1);
       }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccCols;
       const float bias_m = (p.bias && p.bias_along_m && valid) ? p.bias[row] : 0.f;
-      for (int c = 0; c < p.block_n; c += 32) {
+
+      auto process = [&](int c, const uint4 (&res)[4]) {
         uint32_t v[32];
-        tmem_ld32(t_row + c, v);
+        tmem_ld32(t_row + c * 32, v);
         tmem_ld_wait();
-        const int n0 = n_blk * p.block_n + c;
-        if (!valid || n0 >= p.N) continue;
+        const int n0 = ncol0 + c * 32;
+        if (!valid || n0 >= p.N) return;
         if (p.act == 2) {
           // GEGLU: columns interleaved (h, g) -> 16 outputs
           const int o0 = n0 >> 1;
@@ -203,14 +278,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 #pragma unroll
           for (int g8 = 0; g8 < 2; ++g8) {
             if (n0 + g8 * 16 >= p.N) break;
-            uint4 st;
-            st.x = pack_bf16(o[g8 * 8 + 0], o[g8 * 8 + 1]);
-            st.y = pack_bf16(o[g8 * 8 + 2], o[g8 * 8 + 3]);
-            st.z = pack_bf16(o[g8 * 8 + 4], o[g8 * 8 + 5]);
-            st.w = pack_bf16(o[g8 * 8 + 6], o[g8 * 8 + 7]);
-            *reinterpret_cast<uint4*>(op + g8 * 8) = st;
+            uint4 stv;
+            stv.x = pack_bf16(o[g8 * 8 + 0], o[g8 * 8 + 1]);
+            stv.y = pack_bf16(o[g8 * 8 + 2], o[g8 * 8 + 3]);
+            stv.z = pack_bf16(o[g8 * 8 + 4], o[g8 * 8 + 5]);
+            stv.w = pack_bf16(o[g8 * 8 + 6], o[g8 * 8 + 7]);
+            *reinterpret_cast<uint4*>(op + g8 * 8) = stv;
           }
-          continue;
+          return;
         }
 #pragma unroll
         for (int g8 = 0; g8 < 4; ++g8) {
@@ -245,49 +320,100 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             for (int j = 0; j < 8; ++j) x[j] = quick_gelu_f(x[j]);
           }
           if (p.residual) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ld_res + n));
             float2 f;
-            f = unpack_bf16(r.x); x[0] += f.x; x[1] += f.y;
-            f = unpack_bf16(r.y); x[2] += f.x; x[3] += f.y;
-            f = unpack_bf16(r.z); x[4] += f.x; x[5] += f.y;
-            f = unpack_bf16(r.w); x[6] += f.x; x[7] += f.y;
+            f = unpack_bf16(res[g8].x); x[0] += f.x; x[1] += f.y;
+            f = unpack_bf16(res[g8].y); x[2] += f.x; x[3] += f.y;
+            f = unpack_bf16(res[g8].z); x[4] += f.x; x[5] += f.y;
+            f = unpack_bf16(res[g8].w); x[6] += f.x; x[7] += f.y;
           }
           if (p.out_fp32) {
             float* op = reinterpret_cast<float*>(p.out) + row * p.ld_out + n;
             *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
             *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
           } else {
-            uint4 st;
-            st.x = pack_bf16(x[0], x[1]); st.y = pack_bf16(x[2], x[3]);
-            st.z = pack_bf16(x[4], x[5]); st.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n) = st;
+            uint4 stv;
+            stv.x = pack_bf16(x[0], x[1]); stv.y = pack_bf16(x[2], x[3]);
+            stv.z = pack_bf16(x[4], x[5]); stv.w = pack_bf16(x[6], x[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n) = stv;
           }
+        }
+      };
+      for (int c = chalf; c < nchunks; c += 4) {
+        process(c, r0);
+        if (p.residual && c + 4 < nchunks) load_res(c + 4, r0);
+        if (c + 2 < nchunks) {
+          process(c + 2, r1);
+          if (p.residual && c + 6 < nchunks) load_res(c + 6, r1);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[acc]);
+      if (lane == 0) {
+        if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+        else mbar_arrive(&bars->tmem_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (csize > 1) cluster_sync(); else __syncthreads();   // no CTA may exit while peers can still multicast into it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-static int pick_block_n(long long m_tiles, long long N, int sms) {
-  int best = 32;
+// Joint choice of the N tile and the cluster shape from a cycle model per 64-deep k-block:
+//   tensor pipe  2*bn cycles (4 MMAs of 128 x bn x 16 at 8192 FLOP/clk/SM)
+//   L2 -> SMEM   (16384/cn + 128*bn/cm) / 64 cycles (64 B/clk/SM)
+// times the number of waves of (super-)tiles over the co-resident clusters, plus per-tile epilogue/fixed cost.
+struct TileChoice { int bn, cm, cn, pair; };
+static int max_clusters_for(int csize) {
+  static int cache[5] = {-1, -1, -1, -1, -1};
+  if (csize < 1 || csize > 4) return 0;
+  if (cache[csize] >= 0) return cache[csize];
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(num_sms() / csize * csize);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = 200 * 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  cache[csize] = n;
+  return n;
+}
+// Joint choice of the N tile and of 1-CTA vs CTA-pair execution from a cycle model per 64-deep k-block:
+//   tensor pipe   2*bn cycles per SM (128 x bn x 64 MACs at 4096 MAC/clk/SM)
+//   SMEM ingest   (16384 + 128*bn) / 57 cycles for a 1-CTA tile, (16384 + 64*bn) / 57 for a pair (each CTA stages only
+//                 half of B) — ~57 B/clk/SM is what TMA delivers into one SM (measured; multicast does not raise it)
+// times the waves of tiles over the co-resident CTAs/pairs, plus a per-tile epilogue/fixed cost.
+static TileChoice pick_tiling(long long m_tiles, long long N, int num_kb, int sms, int force_pair) {
+  TileChoice best = {32, 1, 1, 0};
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
-    const long long tiles = m_tiles * ((N + bn - 1) / bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    const double per_tile = fmax(bn / 2.0, 32.0 + bn / 4.0) + 24.0;   // MMA-bound vs smem-bound + fixed overhead
-    const double cost = waves * per_tile;
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  for (int pair = 0; pair < 2; ++pair) {
+    if (pair != (force_pair > 0 ? 1 : 0)) continue;   // measured: the pair variant is not faster → opt-in only
+    const int units = pair ? max_clusters_for(2) : sms;
+    if (units <= 0) continue;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      const long long n_tiles = (N + bn - 1) / bn;
+      const long long work = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+      const long long waves = (work + units - 1) / units;
+      // per-tile time ~ k-blocks x max(tensor pipe 2*bn cycles, smem-bandwidth floor) + epilogue/fixed cost (tuned on B200)
+      const double t_kb = fmax(2.0 * bn, 128.0 + bn);
+      const double cost = waves * (t_kb * num_kb + 20.0 * num_kb + 2000.0 + 10.0 * bn);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, pair ? 2 : 1, 1, pair}; }
+    }
   }
   return best;
 }
@@ -365,12 +491,38 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     }
   }
   p.M = (int)M;
+  p.batch = d->mode == 0 ? 1 : d->batch;
   FD_REQUIRE(M > 0 && M < (1ll << 31), "fd_gemm: bad M");
   const int sms = num_sms();
-  p.block_n = d->block_n ? d->block_n : pick_block_n(p.m_tiles, d->N, sms);
+  static int env_cm = -1, env_cn = -1, env_bn = -1, env_pair = -1;
+  if (env_cm < 0) {
+    const char* e = getenv("FD_GEMM_CLUSTER");          // tuning override "cm,cn": TMA-multicast cluster (experiment)
+    env_cm = env_cn = 0;
+    if (e) sscanf(e, "%d,%d", &env_cm, &env_cn);
+    const char* b = getenv("FD_GEMM_BN");
+    env_bn = b ? atoi(b) : 0;
+    const char* pr = getenv("FD_GEMM_PAIR");             // 0 / 1 forces 1-CTA / CTA-pair tiles
+    env_pair = pr ? atoi(pr) : -1;
+  }
+  TileChoice tc = pick_tiling(p.m_tiles, d->N, p.taps * p.kb_per_tap, sms, env_pair);
+  if (env_cm > 0 && env_cn > 0) {
+    tc = pick_tiling(p.m_tiles, d->N, p.taps * p.kb_per_tap, sms, 0);
+    tc.cm = env_cm; tc.cn = env_cn; tc.pair = 0;
+  }
+  if (env_bn > 0) tc.bn = env_bn;
+  if (d->block_n) tc.bn = d->block_n;
+  p.block_n = tc.bn; p.cm = tc.cm; p.cn = tc.cn; p.pair = tc.pair;
   FD_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "fd_gemm: bad block_n %d", p.block_n);
   p.n_tiles = (int)((d->N + p.block_n - 1) / p.block_n);
-  const int stage_bytes = kATileBytes + p.block_n * kBlockK * 2;
+  p.m_super = (p.m_tiles + p.cm - 1) / p.cm;
+  p.n_super = (p.n_tiles + p.cn - 1) / p.cn;
+  // A part geometry (1/cn of the 128-row tile per CTA of a tile row)
+  int a_box_rows = kBlockM / p.cn, a_bw = p.bw, a_bh = p.bh;
+  if (p.mode != 0 && p.cn == 2) {
+    if (p.bh >= 2) { a_bh = p.bh / 2; p.a_part_dy = a_bh; p.a_part_dx = 0; }
+    else { a_bw = p.bw / 2; p.a_part_dy = 0; p.a_part_dx = a_bw; }
+  }
+  const int stage_bytes = kATileBytes + (p.pair ? p.block_n / 2 : p.block_n) * kBlockK * 2;
   const int smem_budget = 227 * 1024 - (int)sizeof(PipeBarriers) - 64;
   p.stages = smem_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
@@ -381,7 +533,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     for (int s = 0; s < nsrc; ++s) {
       uint64_t dims[2] = {(uint64_t)d->a_cols[s], (uint64_t)M};
       uint64_t str[1] = {(uint64_t)d->a_ld[s] * 2};
-      uint32_t box[2] = {kBlockK, kBlockM};
+      uint32_t box[2] = {kBlockK, (uint32_t)a_box_rows};
       if (encode_tensor_map(&p.amap[s], d->a[s], 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                             CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
@@ -390,7 +542,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
       const uint64_t ld = (uint64_t)d->a_ld[s];
       uint64_t dims[4] = {(uint64_t)d->a_cols[s], (uint64_t)d->in_w, (uint64_t)d->in_h, (uint64_t)d->batch};
       uint64_t str[3] = {ld * 2, ld * 2 * d->in_w, ld * 2 * d->in_w * d->in_h};
-      uint32_t box[4] = {kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+      uint32_t box[4] = {kBlockK, (uint32_t)a_bw, (uint32_t)a_bh, 1};
       if (encode_tensor_map(&p.amap[s], d->a[s], 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                             CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
@@ -403,7 +555,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
         const uint8_t* base = (const uint8_t*)d->a[0] + ((uint64_t)py * d->in_w + px) * ld * 2;
         uint64_t dims[4] = {(uint64_t)c0, (uint64_t)ww, (uint64_t)hh, (uint64_t)d->batch};
         uint64_t str[3] = {ld * 4, ld * 4 * d->in_w, ld * 2 * d->in_w * d->in_h};
-        uint32_t box[4] = {kBlockK, (uint32_t)p.bw, (uint32_t)p.bh, 1};
+        uint32_t box[4] = {kBlockK, (uint32_t)a_bw, (uint32_t)a_bh, 1};
         if (encode_tensor_map(&p.amap[py * 2 + px], base, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                               CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
       }
@@ -411,7 +563,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   {
     uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->N};
     uint64_t str[1] = {(uint64_t)ktot * 2};
-    uint32_t box[2] = {kBlockK, (uint32_t)p.block_n};
+    uint32_t box[2] = {kBlockK, (uint32_t)(p.block_n / p.cm)};
     if (encode_tensor_map(&p.bmap, d->b, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                           CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
   }
@@ -424,12 +576,32 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sms ? tiles : sms;
-  gemm_tcgen05_kernel<<<grid, kThreads, smem_bytes, stream>>>(p);
+  const int csize = p.cm * p.cn;
+  const int num_super = p.m_super * p.n_super;
+  if (csize == 1) {
+    const int grid = num_super < sms ? num_super : sms;
+    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+  } else {
+    const int maxc = max_clusters_for(csize);
+    FD_REQUIRE(maxc > 0, "fd_gemm: no co-resident clusters of %d CTAs available", csize);
+    const int clusters = num_super < maxc ? num_super : maxc;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(clusters * csize);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (p.pair) FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p));
+    else FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p));
+  }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -3,16 +3,8 @@ import ctypes as C, os, sys, time
 import torch
 import torch.nn.functional as F
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-class GemmDesc(C.Structure):
-    _fields_ = [
-        ("a", C.c_void_p * 2), ("a_cols", C.c_int64 * 2), ("a_ld", C.c_int64 * 2), ("b", C.c_void_p),
-        ("M", C.c_int64), ("N", C.c_int64), ("mode", C.c_int32), ("batch", C.c_int32), ("in_h", C.c_int32),
-        ("in_w", C.c_int32), ("pad_lo", C.c_int32), ("act", C.c_int32), ("bias_along_m", C.c_int32),
-        ("out_fp32", C.c_int32), ("bias", C.c_void_p), ("rowbias", C.c_void_p), ("rows_per_batch", C.c_int64),
-        ("residual", C.c_void_p), ("ld_res", C.c_int64), ("out", C.c_void_p), ("ld_out", C.c_int64),
-        ("alpha", C.c_float), ("block_n", C.c_int32),
-    ]
-lib = C.CDLL(os.environ.get("FD_LIB", "faithdiff_dev_b200/libfaithdiff_b200.so"))
+from faithdiff_dev_b200._lib import GemmDesc
+lib = C.CDLL("faithdiff_dev_b200/libfaithdiff_b200.so")
 lib.fd_last_error.restype = C.c_char_p
 lib.fd_gemm.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
 dev = "cuda"
