@@ -129,6 +129,8 @@ class FaithDiffStableDiffusionXLPipeline:
     def set_distributed(self, rank, world_size, process_group=None):
         """Multi-GPU: tiles are sharded round-robin over ranks; one all-reduce of the fp32 canvas per step."""
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
+        from . import vae as _vae
+        _vae.DIST.update(rank=rank, world=world_size, group=process_group)
 
     def check_inputs(self, lr_img, prompt, height, width, prompt_embeds, negative_prompt, negative_prompt_embeds,
                      pooled_prompt_embeds, negative_pooled_prompt_embeds):

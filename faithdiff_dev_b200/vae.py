@@ -54,15 +54,44 @@ def _count_blocks(sd, prefix):
     return n
 
 
-def _tiled(x, fn, tile_in, stride, blend_extent, row_limit):
+# multi-GPU context for the one-time tiled stages (set by the pipeline): tiles are independent up to the seam blend, so
+# rank r computes tiles r, r+W, … and every tile is broadcast from its owner before the (cheap, replicated) seam blend
+DIST = {"rank": 0, "world": 1, "group": None}
+
+
+def _down8(n):
+    for _ in range(3):
+        n = (n - 2) // 2 + 1          # F.pad(0,1,0,1) + conv3x3 stride 2 pad 0
+    return n
+
+
+def _tiled(x, fn, tile_in, stride, blend_extent, row_limit, out_shape=None):
     """Shared structure of Encoder.tiled_encode (…extension.py:164-190) and AutoencoderKL.tiled_encode/decode:
     row-major tiles, in-place seam cross-fade with the tile above then the tile to the left, crop, concat."""
     rows = []
+    n = 0
+    world, rank = DIST["world"], DIST["rank"]
+    shard = world > 1 and out_shape is not None
+    flat = []
     for i in range(0, x.shape[2], stride):
         row = []
         for j in range(0, x.shape[3], stride):
-            row.append(fn(x[:, :, i:i + tile_in, j:j + tile_in].contiguous()))
+            src = x[:, :, i:i + tile_in, j:j + tile_in]
+            if not shard or n % world == rank:
+                tile = fn(src.contiguous())
+            else:
+                tile = torch.empty(out_shape(src.shape), device=x.device, dtype=x.dtype)
+            row.append(tile)
+            flat.append((n % world, tile))
+            n += 1
         rows.append(row)
+    if shard:
+        # exchange AFTER all local tiles are enqueued, so the ranks compute concurrently (a broadcast placed between the
+        # computes would serialise the ranks on the stream)
+        grp = DIST["group"]
+        for owner, tile in flat:
+            src_rank = torch.distributed.get_global_rank(grp, owner) if grp is not None else owner
+            torch.distributed.broadcast(tile, src=src_rank, group=grp)
     out_rows = []
     for i, row in enumerate(rows):
         out = []
@@ -114,7 +143,9 @@ class Encoder:
         stride = int(self.tile_sample_min_size * (1 - self.tile_overlap_factor))
         blend_extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
         row_limit = self.tile_latent_min_size - blend_extent
-        return _tiled(x, self.encode, self.tile_sample_min_size, stride, blend_extent, row_limit)
+        c_out = self.mid[2].cout
+        return _tiled(x, self.encode, self.tile_sample_min_size, stride, blend_extent, row_limit,
+                      out_shape=lambda s: (s[0], c_out, _down8(s[2]), _down8(s[3])))
 
     def forward(self, sample):
         if not sample.is_cuda:
@@ -220,7 +251,8 @@ class AutoencoderKL:
             stride = int(self.tile_sample_min_size * (1 - self.tile_overlap_factor))
             blend_extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
             row_limit = self.tile_latent_min_size - blend_extent
-            moments = _tiled(x, self._encode_moments, self.tile_sample_min_size, stride, blend_extent, row_limit)
+            moments = _tiled(x, self._encode_moments, self.tile_sample_min_size, stride, blend_extent, row_limit,
+                             out_shape=lambda s: (s[0], 2 * self.config.latent_channels, _down8(s[2]), _down8(s[3])))
         else:
             moments = self._encode_moments(x)
         return _EncOut(DiagonalGaussianDistribution(moments))
@@ -247,7 +279,9 @@ class AutoencoderKL:
             stride = int(self.tile_latent_min_size * (1 - self.tile_overlap_factor))
             blend_extent = int(self.tile_sample_min_size * self.tile_overlap_factor)
             row_limit = self.tile_sample_min_size - blend_extent
-            dec = _tiled(z, self._decode_tile, self.tile_latent_min_size, stride, blend_extent, row_limit)
+            up = 2 ** (len(self.config.block_out_channels) - 1)
+            dec = _tiled(z, self._decode_tile, self.tile_latent_min_size, stride, blend_extent, row_limit,
+                         out_shape=lambda s: (s[0], self.config.out_channels, s[2] * up, s[3] * up))
         else:
             dec = self._decode_tile(z)
         if not return_dict:

@@ -1,0 +1,44 @@
+"""Dev (torchrun, N GPUs): N-rank pipeline result == 1-rank result (tiny config) + timing of the full-size 4K path."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+import faithdiff_dev_b200 as fd
+from faithdiff_dev_b200 import arch
+from oracle import faithdiff_oracle as O
+BF = torch.bfloat16
+cfg = O.TINY_UNET_CONFIG
+sd = arch.random_state_dict(arch.unet_param_shapes(cfg, lq_channels=64, encoder_channels=(32, 64, 64, 64)), seed=1, device="cuda")
+unet = fd.UNet2DConditionModel(**cfg); unet.load_state_dict(sd)
+vae = fd.AutoencoderKL(**O.TINY_VAE_CONFIG); vae.load_state_dict(arch.random_state_dict(arch.vae_param_shapes(dict(O.TINY_VAE_CONFIG, layers_per_block=2, latent_channels=4)), seed=2))
+def make_pipe(dist):
+    p = fd.FaithDiffStableDiffusionXLPipeline(vae, unet.denoise_encoder, None, None, None, None, unet, fd.EulerDiscreteScheduler(), fd.DDPMScheduler())
+    if dist: p.set_distributed(rank, world)
+    else: p.set_distributed(0, 1)
+    return p
+for e in (unet.denoise_encoder,):
+    e.tile_sample_min_size, e.tile_latent_min_size, e.use_tiling = 128, 16, True
+vae.enable_tiling()
+g = torch.Generator().manual_seed(7)
+pe, npe = torch.randn(1, 77, 256, generator=g), torch.randn(1, 77, 256, generator=g)
+pp, npp = torch.randn(1, 64, generator=g), torch.randn(1, 64, generator=g)
+lr = O.synthetic_lq_image(328, 232, seed=0)
+lat = torch.randn(1, 4, 29, 41, generator=g).to(BF).cuda()
+def run(p):
+    torch.manual_seed(3)
+    return p(lr_img=lr, prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pp, negative_pooled_prompt_embeds=npp,
+             num_inference_steps=3, start_point="lr", height=232, width=328, overlap=0.5, guidance_scale=5.0, target_size=(128, 128),
+             latents=lat.clone(), output_type="u8").images[0]
+a = run(make_pipe(False)).float()
+b = run(make_pipe(True)).float()
+mse = ((a - b) ** 2).mean().item()
+psnr = 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
+allp = [None] * world
+torch.distributed.all_gather_object(allp, (psnr, float((a - b).abs().max())))
+if rank == 0:
+    print("world=%d: PSNR(N-rank vs 1-rank) per rank:" % world, allp, flush=True)
+    assert min(p for p, _ in allp) > 45, allp
+torch.distributed.barrier()
+torch.distributed.destroy_process_group()

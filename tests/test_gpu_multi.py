@@ -1,0 +1,22 @@
+"""-m gpu (needs >= 2 GPUs, skipped otherwise): the N-rank NCCL path of the pipeline (tile sharding + per-step canvas
+all-reduce + sharded tiled encoder/VAE) reproduces the 1-rank result.  Runs scripts/dev_multigpu_check.py under torchrun."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_pipeline_matches_single_rank():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "scripts", "dev_multigpu_check.py")], capture_output=True, text=True,
+                       timeout=800, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PSNR(N-rank vs 1-rank)" in r.stdout
