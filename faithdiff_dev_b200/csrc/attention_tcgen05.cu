@@ -100,31 +100,39 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                       // query row within the block
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    float o[64];
+    uint64_t o2[32];                                      // running output row, packed fp32x2
 #pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
+    for (int i = 0; i < 32; ++i) o2[i] = 0ull;
     float m = -INFINITY, l = 0.f;
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
+    const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
       const int kv0 = j * kKV;
-      // pass 1: row max
+      const bool full = kv0 + kKV <= p.lk;               // only the last block can need masking
+      // pass 1: row max (3-input max halves the instruction count)
       float mx = m;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(t_lane + c * 32, v);
         tmem_ld_wait();
+        if (full) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (kv0 + c * 32 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; i += 2) mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
       const float alpha = fast_exp2((m - mx) * p.scale_log2);
-      const float mxs = mx * p.scale_log2;
-      float lsum = 0.f;
-      // pass 2: p = exp2(s*scale - max*scale) -> bf16 -> swizzled smem
+      const float nmxs = -mx * p.scale_log2;
+      const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
+      uint64_t lsum2 = 0ull;
+      // pass 2: p = exp2(s*scale - max*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -132,10 +140,18 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
         tmem_ld_wait();
         float e[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pv = (kv0 + c * 32 + i < p.lk) ? fast_exp2(__uint_as_float(v[i]) * p.scale_log2 - mxs) : 0.f;
-          e[i] = pv;
-          lsum += pv;
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scale2, nmxs2);
+          float a0, a1;
+          unpack_f2(t, a0, a1);
+          a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower: the loop is
+          a1 = fast_exp2(a1);      //  issue-bound, not MUFU-bound, and the extra converts cost more than they save)
+          if (!full) {
+            if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
+            if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
+          }
+          e[i] = a0; e[i + 1] = a1;
+          lsum2 = add_f2(lsum2, pack_f2(a0, a1));
         }
         uint8_t* half_base = prow + (c >> 1) * kTile;
 #pragma unroll
@@ -147,15 +163,20 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
           *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
         }
       }
-      l = l * alpha + lsum;
+      float ls0, ls1;
+      unpack_f2(lsum2, ls0, ls1);
+      l = l * alpha + (ls0 + ls1);
       m = mx;
       fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
-      // rescale the running output while the PV MMA runs
+      // rescale the running output while the PV MMA runs; skipped when no row of the warp raised its max
+      if (__any_sync(0xffffffffu, alpha != 1.f)) {
+        const uint64_t al2 = pack_f2(alpha, alpha);
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] *= alpha;
+        for (int i = 0; i < 32; ++i) o2[i] = mul_f2(o2[i], al2);
+      }
       mbar_wait(&bars->o_full, j & 1);
       tc_fence_after();
 #pragma unroll
@@ -164,10 +185,14 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
         tmem_ld32(t_lane + 128 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += __uint_as_float(v[i]);
+        for (int i = 0; i < 32; i += 2)
+          o2[c * 16 + (i >> 1)] = add_f2(o2[c * 16 + (i >> 1)], pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
       }
       tc_fence_before();
     }
+    float o[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) unpack_f2(o2[i], o[2 * i], o[2 * i + 1]);
     const int qi = qblk * kQ + r;
     if (qi < p.lq) {
       const float inv = 1.f / l;

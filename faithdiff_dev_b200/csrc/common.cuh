@@ -251,6 +251,43 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (sm_100): two fp32 lanes per instruction on the FMA pipe
+__device__ __forceinline__ uint64_t pack_f2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// two exponentials per MUFU op: exp2 on an f16x2 pair (inputs <= 0, results in (0,1]; the consumer rounds to bf16 anyway)
+__device__ __forceinline__ void exp2_pair_f16(float a0, float a1, float& e0, float& e1) {
+  asm("{\n.reg .b32 h;\n.reg .b16 lo, hi;\n"
+      "cvt.rn.f16x2.f32 h, %3, %2;\n"          // h = {hi: a1, lo: a0}
+      "ex2.approx.f16x2 h, h;\n"
+      "mov.b32 {lo, hi}, h;\n"
+      "cvt.f32.f16 %0, lo;\ncvt.f32.f16 %1, hi;\n}"
+      : "=f"(e0), "=f"(e1)
+      : "f"(a0), "f"(a1));
+}
+__device__ __forceinline__ float max3_f(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.f + __expf(-1.702f * x)); }

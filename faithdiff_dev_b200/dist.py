@@ -11,16 +11,34 @@ def shard_tiles(num_tiles, rank, world_size):
     return list(range(rank, num_tiles, world_size))
 
 
-def plan_launch_groups(my_tiles, sizes):
-    """Greedy split of a rank's tile list into launch groups using the available graph batch sizes (descending)."""
-    groups, i = [], 0
-    sizes = sorted(set(sizes), reverse=True)
-    while i < len(my_tiles):
-        left = len(my_tiles) - i
-        nb = next((s for s in sizes if s <= left), sizes[-1])
-        groups.append(my_tiles[i:i + nb])
-        i += nb
-    return groups
+# measured cost (ms) of one CUDA-graph replay of the UNet tile-step for n tiles per launch on B200 (profiles/): batching
+# amortises prologues and improves wave quantisation up to ~3 tiles
+REPLAY_COST_MS = {1: 27.4, 2: 41.1, 3: 57.8, 4: 79.3}
+
+
+def plan_launch_groups(my_tiles, sizes, costs=None):
+    """Split a rank's tile list into launch groups (sizes drawn from `sizes`) minimising the summed replay cost
+    (dynamic programme over the tile count); groups keep the tile order."""
+    costs = costs or REPLAY_COST_MS
+    sizes = sorted({s for s in sizes if s >= 1} | {1})
+    n = len(my_tiles)
+    best = [0.0] + [float("inf")] * n
+    choice = [0] * (n + 1)
+    for i in range(1, n + 1):
+        for s in sizes:
+            if s <= i:
+                c = best[i - s] + costs.get(s, costs[max(costs)] * s / max(costs))
+                if c < best[i] - 1e-9:
+                    best[i], choice[i] = c, s
+    groups, i = [], n
+    while i > 0:
+        groups.append(choice[i])
+        i -= choice[i]
+    out, pos = [], 0
+    for g in sorted(groups, reverse=True):
+        out.append(my_tiles[pos:pos + g])
+        pos += g
+    return out
 
 
 def exchange_canvas(numerator, group=None):

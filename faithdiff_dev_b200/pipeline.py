@@ -94,7 +94,7 @@ class FaithDiffStableDiffusionXLPipeline:
         self.watermark = None
         self.device = torch.device("cuda")
         self.rank, self.world_size, self.process_group = 0, 1, None
-        self.tiles_per_launch = 2
+        self.tiles_per_launch = 4          # upper bound; the launch plan mixes group sizes 1..N by measured cost
         self.use_cuda_graph = True
         self._graphs = {}
 
@@ -253,8 +253,7 @@ class FaithDiffStableDiffusionXLPipeline:
         ids_all = torch.tensor([[original_size[0], original_size[1], i, j, target_size[0], target_size[1]] for i, j in idx],
                                dtype=torch.float32).to(dt).to(torch.float32)   # rounded through the working dtype
         temb_table = unet.time_embedding_table(ts, te, ids_all.to(dev))          # [S, T, 2, ΣC]: all (step, tile) biases
-        sizes = sorted({max(1, min(self.tiles_per_launch, len(mine))), 1}, reverse=True)
-        groups = plan_launch_groups(mine, sizes)
+        groups = plan_launch_groups(mine, range(1, max(1, self.tiles_per_launch) + 1))
         gbase = (k1, k2, bool(add_sample), lk, self.use_cuda_graph)
         if self._graphs.get("key") != gbase:
             self._graphs = {"key": gbase}
