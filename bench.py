@@ -318,8 +318,15 @@ def main():
         r = roofline_pass(pipe, torch, ops)
         if r:
             ach = r["flops"] / r["seconds"] / 1e12
+            traffic, traffic_note = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+                traffic = tj["dram__bytes_read"] + tj["dram__bytes_write"]
+                traffic_note = "%s: DRAM %d B vs algorithmic %d B (%s)" % (tj["launch"], traffic, tj["algorithmic_bytes"], tj["source"])
+            except Exception:
+                pass
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": which,
+                    "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
                     "how": "executed FLOPs of all %d fd_gemm launches of one %d-tile UNet evaluation / their summed CUDA-event "
                            "durations (instrumented eager pass after the timed region)" % (r["launches"], r["tiles"]),
                     "avg_launch_us": r["seconds"] / r["launches"] * 1e6,
