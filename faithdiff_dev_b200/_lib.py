@@ -55,6 +55,7 @@ _SIGS = {
     "fd_tile_blend": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
     "fd_cfg_euler_blend": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp],
     "fd_tile_accumulate": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
+    "fd_unit_accumulate": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
     "fd_scale_div": [vp, vp, i32, f32, i64, vp],
     "fd_seam_blend": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],

@@ -117,6 +117,35 @@ __global__ void tile_blend_kernel(const BlendParams p) {
   }
 }
 
+// (tile, CFG-branch) units — the finer multi-GPU work split.  CFG combine and the Euler update are linear in eps:
+//   x' = x + dt * ((1-g) * eps_uncond + g * eps_text)
+// so every unit deposits  w * coef_u * eps_u  (coef = (1-g)*dt or g*dt) and the branch-0 unit of a tile also deposits w * x.
+// Summed over all ranks (all-reduce) this is the blend numerator; fp32 combination (no intermediate bf16 roundings).
+__global__ void unit_accumulate_kernel(const void* __restrict__ x_tiles, const void* __restrict__ eps_units, int dtype,
+                                       const double* __restrict__ weights, const int* __restrict__ org,
+                                       const int* __restrict__ unit_tile, const float* __restrict__ unit_coef,
+                                       const int* __restrict__ unit_addx, int nunits, int c, int h, int w, int k1, int k2,
+                                       float* __restrict__ canvas_num) {
+  const long long total = (long long)c * h * w;
+  const long long plane = (long long)k1 * k2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int ch = (int)(i / ((long long)w * h));
+    double acc = (double)canvas_num[i];
+    for (int u = 0; u < nunits; ++u) {
+      const int t = unit_tile[u];
+      const int ly = y - org[2 * t], lx = x - org[2 * t + 1];
+      if (ly < 0 || ly >= k1 || lx < 0 || lx >= k2) continue;
+      const long long off = (long long)ly * k2 + lx;
+      float v = __fmul_rn(unit_coef[u], load_lowp(eps_units, dtype, ((long long)u * c + ch) * plane + off));
+      if (unit_addx[u]) v = __fadd_rn(v, load_lowp(x_tiles, dtype, ((long long)t * c + ch) * plane + off));
+      acc = __dadd_rn(acc, __dmul_rn((double)v, weights[off]));
+    }
+    canvas_num[i] = __double2float_rn(acc);
+  }
+}
+
 __global__ void canvas_finalize_kernel(const float* __restrict__ num, const float* __restrict__ count, float* __restrict__ out,
                                        void* lowp, int lowp_dtype, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -240,6 +269,19 @@ extern "C" int fd_seam_blend(const void* a, void* b, int32_t dtype, int32_t c, i
 extern "C" int fd_scale_div(const void* x, void* out, int32_t dtype, float div, int64_t n, void* stream_) {
   FD_REQUIRE(x && out && dtype >= 0 && dtype <= 2, "fd_scale_div: bad arguments");
   scale_div_kernel<<<blend_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, out, dtype, 1.0f / div, n);
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+                                  const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef,
+                                  const int32_t* unit_addx, int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1,
+                                  int32_t k2, float* canvas_num, void* stream_) {
+  FD_REQUIRE(x_tiles && eps_units && weights && origins_ij && unit_tile && unit_coef && unit_addx && canvas_num,
+             "fd_unit_accumulate: null pointer");
+  unit_accumulate_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
+      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

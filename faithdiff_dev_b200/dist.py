@@ -41,6 +41,40 @@ def plan_launch_groups(my_tiles, sizes, costs=None):
     return out
 
 
+def shard_units(num_tiles, rank, world_size):
+    """(tile, CFG-branch) units u = 2*tile + branch, split into contiguous balanced ranges: rank r owns
+    [r*U/W, (r+1)*U/W).  Contiguity keeps both branches of a tile on one rank wherever possible (shared stem)."""
+    U = 2 * num_tiles
+    lo, hi = rank * U // world_size, (rank + 1) * U // world_size
+    return list(range(lo, hi))
+
+
+# measured replay cost (ms) by number of SAMPLES (= units) per launch; odd sizes interpolated
+UNIT_REPLAY_COST_MS = {1: 18.0, 2: 27.4, 3: 34.5, 4: 41.1, 5: 49.5, 6: 57.8, 7: 68.5, 8: 79.3}
+
+
+def plan_unit_groups(units, max_samples=8):
+    """Split a contiguous unit range into consecutive launch groups minimising the summed replay cost."""
+    n = len(units)
+    best = [0.0] + [float("inf")] * n
+    choice = [0] * (n + 1)
+    for i in range(1, n + 1):
+        for sz in range(1, min(max_samples, i) + 1):
+            c = best[i - sz] + UNIT_REPLAY_COST_MS[sz]
+            if c < best[i] - 1e-9:
+                best[i], choice[i] = c, sz
+    sizes, i = [], n
+    while i > 0:
+        sizes.append(choice[i])
+        i -= choice[i]
+    sizes.reverse()
+    out, pos = [], 0
+    for sz in sizes:
+        out.append(units[pos:pos + sz])
+        pos += sz
+    return out
+
+
 def exchange_canvas(numerator, group=None):
     """The per-step exchange of the overlap-region accumulation: in-place sum over ranks."""
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:

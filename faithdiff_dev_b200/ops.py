@@ -266,6 +266,13 @@ def tile_accumulate(tiles, eps, weights, origins, canvas_num, guidance=0.0, sigm
                                  sigma, sigma_next, _p(canvas_num), _stream()), "fd_tile_accumulate")
 
 
+def unit_accumulate(x_tiles, eps_units, weights, origins, unit_tile, unit_coef, unit_addx, canvas_num):
+    U, c, k1, k2 = eps_units.shape
+    _, _, h, w = canvas_num.shape
+    check(lib.fd_unit_accumulate(_p(x_tiles), _p(eps_units), _DT[x_tiles.dtype], _p(weights), _p(origins), _p(unit_tile), _p(unit_coef),
+                                 _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()), "fd_unit_accumulate")
+
+
 def canvas_finalize(num, count, lowp_dtype):
     out = torch.empty_like(num)
     lowp = torch.empty(num.shape, device=num.device, dtype=lowp_dtype)

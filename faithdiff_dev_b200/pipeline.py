@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from .blocks import BF16
-from .dist import exchange_canvas, plan_launch_groups, shard_tiles
+from .dist import exchange_canvas, plan_launch_groups, plan_unit_groups, shard_tiles, shard_units
 from .tiling import LocalAttention, gaussian_weights, tile_origins
 
 
@@ -27,21 +27,27 @@ class _Cfg(dict):
 
 
 class TileStepGraph:
-    """One CUDA graph = the UNet evaluation of `nb` latent tiles (each a CFG pair): FaithDiff stem once per tile (the
-    two CFG halves are identical, pipeline_FaithDiff_tlc.py:1334-1335), trunk on the 2·nb samples.  Replayed for every
-    (step, tile group); per-replay inputs are copied into static buffers.  Removes ~1000 host launches per tile-step."""
+    """One CUDA graph = the UNet evaluation of a launch group of (tile, CFG-branch) samples.  The FaithDiff stem runs once per
+    distinct tile of the group (the CFG halves are identical there, pipeline_FaithDiff_tlc.py:1334-1335); its output rows
+    are gathered into the trunk batch (one row per sample).  `slot_of_sample[s]` = index of sample s's tile among the group's
+    tiles, `branch_of_sample[s]` = 0 (uncond) / 1 (text): both are baked into the graph, all tensors are static buffers that
+    are refilled before each replay.  Removes ~1000 host launches per tile-step."""
 
-    def __init__(self, unet, kv, lk, nb, k1, k2, lowp, add_sample=True, use_graph=True):
+    def __init__(self, unet, kv, lk, slot_of_sample, branch_of_sample, k1, k2, lowp, add_sample=True, use_graph=True):
         dev = unet.device
         c0 = unet.conv_in[0].shape[0]
-        self.unet, self.nb, self.add_sample = unet, nb, add_sample
-        self.scaled = torch.zeros((nb, unet.config.in_channels, k1, k2), device=dev, dtype=lowp)
-        self.cond = torch.zeros((nb, k1, k2, c0), device=dev, dtype=BF16)
-        self.temb = torch.zeros((2 * nb, unet.temb_w.shape[0]), device=dev, dtype=torch.float32)
-        # static text K/V buffers, replicated per tile (the attention kernel indexes K/V rows by sample); a new prompt
-        # is copied in with set_text_kv() — no re-capture
-        self.kv = [[b.repeat(nb, 1).contiguous() for b in tr] for tr in kv]
-        self.lk = lk
+        self.unet, self.add_sample, self.lk = unet, add_sample, lk
+        self.slot_of_sample, self.branch_of_sample = tuple(slot_of_sample), tuple(branch_of_sample)
+        self.ns, self.nt = len(self.slot_of_sample), max(self.slot_of_sample) + 1
+        self.paired = self.slot_of_sample == tuple(i // 2 for i in range(self.ns)) and self.ns % 2 == 0
+        self.gather_idx = torch.tensor(self.slot_of_sample, device=dev, dtype=torch.long)
+        self.scaled = torch.zeros((self.nt, unet.config.in_channels, k1, k2), device=dev, dtype=lowp)
+        self.cond = torch.zeros((self.nt, k1, k2, c0), device=dev, dtype=BF16)
+        self.temb = torch.zeros((self.ns, unet.temb_w.shape[0]), device=dev, dtype=torch.float32)
+        # static text K/V per sample (the attention kernel indexes K/V rows by sample); a new prompt is copied in with
+        # set_text_kv() — no re-capture
+        self.kv = [[torch.zeros((self.ns * lk, b.shape[1]), device=dev, dtype=b.dtype) for b in tr] for tr in kv]
+        self.set_text_kv(kv)
         self.graph = None
         self.replays = 0
         n0 = ops.launch_count()
@@ -55,28 +61,35 @@ class TileStepGraph:
             self.graph = g
 
     def set_text_kv(self, kv):
+        """kv: per transformer block [2*lk, 2C] (rows [0,lk) = uncond text, [lk,2lk) = cond text)."""
+        lk = self.lk
         for dst_tr, src_tr in zip(self.kv, kv):
             for dst, src in zip(dst_tr, src_tr):
-                dst.view(self.nb, -1).copy_(src.reshape(1, -1).expand(self.nb, -1))
+                for s_, b_ in enumerate(self.branch_of_sample):
+                    dst[s_ * lk:(s_ + 1) * lk].copy_(src[b_ * lk:(b_ + 1) * lk])
 
     def _run(self):
         u = self.unet
-        x1 = u.stem(self.scaled, self.cond, add_sample=self.add_sample, groups=self.nb)        # [nb,h,w,c0]
-        x2 = x1.unsqueeze(1).expand(-1, 2, -1, -1, -1).reshape((2 * self.nb,) + tuple(x1.shape[1:])).contiguous()
-        self.eps = u.trunk(x2, self.temb, self.kv, self.lk, self.scaled.dtype)                  # [2nb,4,k1,k2]
+        x1 = u.stem(self.scaled, self.cond, add_sample=self.add_sample, groups=self.nt)        # [nt,h,w,c0]
+        if self.paired:
+            x2 = x1.unsqueeze(1).expand(-1, 2, -1, -1, -1).reshape((self.ns,) + tuple(x1.shape[1:])).contiguous()
+        else:
+            x2 = x1.index_select(0, self.gather_idx)
+        self.eps = u.trunk(x2, self.temb, self.kv, self.lk, self.scaled.dtype)                  # [ns,4,k1,k2]
 
-    def __call__(self, scaled, cond_list, temb, eps_out):
-        n = scaled.shape[0]
-        self.scaled[:n].copy_(scaled)
-        for i, cd in enumerate(cond_list):
+    def __call__(self, scaled_tiles, cond_list, temb_rows, eps_out):
+        """scaled_tiles: list of [4,k1,k2] (one per tile slot); cond_list: per-slot [1,k1,k2,c0]; temb_rows [ns, ΣC];
+        eps_out [ns,4,k1,k2] destination view."""
+        for i, (sc, cd) in enumerate(zip(scaled_tiles, cond_list)):
+            self.scaled[i].copy_(sc)
             self.cond[i].copy_(cd[0])
-        self.temb[:2 * n].copy_(temb.reshape(2 * n, -1))
+        self.temb.copy_(temb_rows)
         if self.graph is not None:
             self.graph.replay()
             self.replays += 1
         else:
             self._run()
-        eps_out.copy_(self.eps.view((self.nb, 2) + tuple(self.eps.shape[1:]))[:n])
+        eps_out.copy_(self.eps)
 
 
 class FaithDiffStableDiffusionXLPipeline:
@@ -245,48 +258,69 @@ class FaithDiffStableDiffusionXLPipeline:
         pe = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(dev, dt)
         te = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], dim=0).to(dev, dt)
         kv, lk = unet.text_kv(pe)
-        mine = shard_tiles(T, self.rank, self.world_size)
+        # work units = (tile, CFG branch); contiguous balanced ranges per rank (a whole CFG pair per launch slot on 1 GPU)
+        my_units = shard_units(T, self.rank, self.world_size)
+        my_tiles = sorted({u // 2 for u in my_units})
         cond = {}
-        for t in mine:                                              # ControlNetConditioningEmbedding: once per tile
+        for t in my_tiles:                                          # ControlNetConditioningEmbedding: once per tile
             i, j = idx[t]
             cond[t] = unet.condition_embed(lq_nhwc[:, i:i + k1, j:j + k2, :].contiguous())
         ids_all = torch.tensor([[original_size[0], original_size[1], i, j, target_size[0], target_size[1]] for i, j in idx],
                                dtype=torch.float32).to(dt).to(torch.float32)   # rounded through the working dtype
         temb_table = unet.time_embedding_table(ts, te, ids_all.to(dev))          # [S, T, 2, ΣC]: all (step, tile) biases
-        groups = plan_launch_groups(mine, range(1, max(1, self.tiles_per_launch) + 1))
+        temb_units = temb_table.reshape(temb_table.shape[0], 2 * T, -1)          # [S, U, ΣC], u = 2*tile + branch
+        if self.world_size == 1:
+            groups = [[u for t in g for u in (2 * t, 2 * t + 1)]
+                      for g in plan_launch_groups(list(range(T)), range(1, max(1, self.tiles_per_launch) + 1))]
+        else:
+            groups = plan_unit_groups(my_units, 2 * max(1, self.tiles_per_launch))
         gbase = (k1, k2, bool(add_sample), lk, self.use_cuda_graph)
         if self._graphs.get("key") != gbase:
             self._graphs = {"key": gbase}
-        for nb in {len(g) for g in groups}:
-            if nb not in self._graphs:
-                self._graphs[nb] = TileStepGraph(unet, kv, lk, nb, k1, k2, dt, add_sample, self.use_cuda_graph)
-            self._graphs[nb].set_text_kv(kv)
+        plans = []
+        for g in groups:
+            gt = sorted({u // 2 for u in g})
+            slot = tuple(gt.index(u // 2) for u in g)
+            branch = tuple(u % 2 for u in g)
+            key = (slot, branch)
+            if key not in self._graphs:
+                self._graphs[key] = TileStepGraph(unet, kv, lk, slot, branch, k1, k2, dt, add_sample, self.use_cuda_graph)
+            plans.append((self._graphs[key], gt, torch.tensor(g, device=dev, dtype=torch.long)))
+        for key, gobj in self._graphs.items():
+            if key != "key":
+                gobj.set_text_kv(kv)
         count = None
         if self.world_size > 1:
             count = torch.zeros(shape, device=dev, dtype=torch.float32)
             ops.tile_accumulate(torch.ones((T, shape[1], k1, k2), device=dev, dtype=torch.float32), None, weights, origins, count)
+            unit_tile = torch.tensor([u // 2 for u in my_units], device=dev, dtype=torch.int32)
+            unit_addx = torch.tensor([1 - u % 2 for u in my_units], device=dev, dtype=torch.int32)
+            # per-step coefficients of the linearised CFG + Euler update: (1-g)*dt for uncond units, g*dt for text units
+            dts = torch.tensor([sch.step_scalars(i)[1] - sch.step_scalars(i)[0] for i in range(len(ts))], dtype=torch.float32)
+            gsel = torch.tensor([guidance_scale if u % 2 else 1.0 - guidance_scale for u in my_units], dtype=torch.float32)
+            unit_coef = (dts[:, None] * gsel[None, :]).to(dev).contiguous()       # [S, U_local]
         ev["enc"].record()
 
         # -- denoising loop (pipeline…:1324-1409)
         s0, _, div0 = sch.step_scalars(0)
         scaled = ops.scale_div(tiles, div0)
-        eps = torch.empty((T, 2) + tuple(tiles.shape[1:]), device=dev, dtype=dt)
+        n_local = len(my_units)
+        eps = torch.empty((n_local,) + tuple(tiles.shape[1:]), device=dev, dtype=dt)     # unit order (pairs when 1 GPU)
         canvas_lowp = None
         for i in range(len(ts)):
             sigma, sigma_next, _ = sch.step_scalars(i)
             next_div = sch.step_scalars(i + 1)[2] if i + 1 < len(ts) else 1.0
             tval = ts[i]
-            for grp in groups:
-                lo, hi, st = grp[0], grp[-1] + 1, self.world_size
-                self._graphs[len(grp)](scaled[lo:hi:st], [cond[t] for t in grp], temb_table[i, lo:hi:st], eps[lo:hi:st])
+            pos = 0
+            for gobj, gt, gu in plans:
+                gobj([scaled[t] for t in gt], [cond[t] for t in gt], temb_units[i].index_select(0, gu), eps[pos:pos + gobj.ns])
+                pos += gobj.ns
             if self.world_size == 1:
-                canvas, canvas_lowp, tiles, scaled = ops.cfg_euler_blend(eps, tiles, weights, origins, h, w, guidance_scale,
-                                                                         sigma, sigma_next, next_div)
+                canvas, canvas_lowp, tiles, scaled = ops.cfg_euler_blend(eps.view((T, 2) + tuple(tiles.shape[1:])), tiles, weights,
+                                                                         origins, h, w, guidance_scale, sigma, sigma_next, next_div)
             else:
                 num = torch.zeros(shape, device=dev, dtype=torch.float32)
-                sel = torch.tensor(mine, device=dev)
-                ops.tile_accumulate(tiles[sel].contiguous(), eps[sel].contiguous(), weights, origins[sel].contiguous(), num,
-                                    guidance_scale, sigma, sigma_next)
+                ops.unit_accumulate(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
                 exchange_canvas(num, self.process_group)
                 canvas, canvas_lowp = ops.canvas_finalize(num, count, dt)
                 tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)

@@ -142,6 +142,12 @@ int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, cons
 int fd_tile_accumulate(const void* tiles, const void* eps_or_null, int32_t dtype, const double* weights,
                        const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2,
                        float guidance, float sigma, float sigma_next, float* canvas_num, void* stream);
+/* finer multi-GPU split into (tile, CFG-branch) units: CFG + Euler are linear in eps, so each unit u deposits
+ * w * (unit_coef[u] * eps_u + unit_addx[u] * x_tile) into the fp32 numerator (coef = (1-g)*dt or g*dt; addx = 1 for the
+ * uncond unit of a tile).  eps_units [nunits,C,k1,k2]; x_tiles [T,C,k1,k2]; unit_tile maps a unit to its tile.            */
+int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+                       const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef, const int32_t* unit_addx,
+                       int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
 int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
                        int32_t lowp_dtype, int64_t n, void* stream);
 /* EulerDiscreteScheduler.scale_model_input (pipeline…:1336): out = x / sqrt(sigma^2+1), rounded to dtype         */
