@@ -176,7 +176,7 @@ def roofline_pass(pipe, torch, ops):
     g = [v for k, v in pipe._graphs.items() if k != "key"]
     if not g:
         return None
-    ts = max(g, key=lambda t: t.nb)
+    ts = max(g, key=lambda t: t.ns)
     rec = []
     orig_gemm, orig_conv = O.gemm, O.conv3x3
 
@@ -200,7 +200,7 @@ def roofline_pass(pipe, torch, ops):
         O.gemm, O.conv3x3 = orig_gemm, orig_conv
     dur = sum(s.elapsed_time(e) for s, e, _ in rec) * 1e-3
     flops = sum(f for _, _, f in rec)
-    return {"launches": len(rec), "seconds": dur, "flops": flops, "tiles": ts.nb}
+    return {"launches": len(rec), "seconds": dur, "flops": flops, "tiles": ts.ns / 2.0}
 
 
 def main():
@@ -327,7 +327,7 @@ def main():
                 pass
             roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": which,
-                    "how": "executed FLOPs of all %d fd_gemm launches of one %d-tile UNet evaluation / their summed CUDA-event "
+                    "how": "executed FLOPs of all %d fd_gemm launches of one %.1f-tile UNet evaluation / their summed CUDA-event "
                            "durations (instrumented eager pass after the timed region)" % (r["launches"], r["tiles"]),
                     "avg_launch_us": r["seconds"] / r["launches"] * 1e6,
                     "unet_tile_step_ms": stage["denoise"] / wl["steps"] / max(1, len(pipe.tlc_vae_latents.idxes)) * world,
@@ -348,7 +348,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": wl["name"], "tiles": len(pipe.tlc_vae_latents.idxes), "tiles_per_launch": args.tiles_per_launch,
-                       "parallelism": "tiles sharded round-robin over %d GPU(s), one NCCL all-reduce of the fp32 canvas per step" % world,
+                       "parallelism": "%d GPU(s): (tile, CFG-branch) units in contiguous balanced ranges, one NCCL all-reduce of the fp32 canvas "
+                                      "per scheduler step; tiled LQ-encoder/VAE tiles round-robin + broadcast" % world,
                        "l2": "no explicit flush: each step streams 5.3 GB of weights 280x plus activations (>> 126 MB L2)",
                        "stage_ms_last_step": {k: round(v, 1) for k, v in stage.items()}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(host_out.numel()),
