@@ -26,6 +26,7 @@ struct GemmKParams {
   int tap_map[9], tap_dy[9], tap_dx[9];
   int out_h, out_w, bw, bh, tiles_x, tiles_per_img, batch;
   int cm, cn, m_super, n_super;      // cluster shape and super-tile grid
+  int group_m;                       // tile rasterisation: concurrent CTAs cover group_m x (148/group_m) tiles
   int pair;                          // 1: CTA pair (cta_group::2, UMMA M=256); cm = 2, cn = 1, B tile split across the pair
   int a_part_dy, a_part_dx;          // conv: pixel offset of A part j inside the tile patch (split along y or x)
   // epilogue
@@ -54,6 +55,19 @@ struct __align__(8) PipeBarriers {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
+
+// Grouped rasterisation of the linear (super-)tile index: consecutive indices walk down a band of `group_m` tile rows before
+// moving to the next tile column, so the ~148 concurrently running CTAs cover a roughly square patch of the output: every
+// A and B tile is then requested by ~12 CTAs at a time instead of one operand being hammered by all of them (L2 hot spot).
+__device__ __forceinline__ void raster_tile(int st, int m_super, int n_super, int group_m, int& mp, int& np) {
+  const int per_group = group_m * n_super;
+  const int g = st / per_group;
+  const int first_m = g * group_m;
+  const int rows = min(m_super - first_m, group_m);
+  const int r = st - g * per_group;
+  mp = first_m + r % rows;
+  np = r / rows;
+}
 
 // kPair = true instantiates the cta_group::2 (CTA-pair, UMMA M=256) variant; a kernel containing cta_group::2
 // instructions can only be launched with an even cluster size, hence two instantiations.
@@ -108,8 +122,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int st = cluster_id; st < num_super; st += num_clusters) {
-        const int m_blk = (st % p.m_super) * p.cm + ci;
-        const int n_blk = (st / p.m_super) * p.cn + cj;
+        int mp_, np_;
+        raster_tile(st, p.m_super, p.n_super, p.group_m, mp_, np_);
+        const int m_blk = mp_ * p.cm + ci;
+        const int n_blk = np_ * p.cn + cj;
         int img = 0, y0 = 0, x0 = 0;
         if (p.mode != 0) {
           img = m_blk / p.tiles_per_img;
@@ -215,8 +231,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
-      const int m_blk = (st % p.m_super) * p.cm + ci;
-      const int n_blk = (st / p.m_super) * p.cn + cj;
+      int mp_, np_;
+      raster_tile(st, p.m_super, p.n_super, p.group_m, mp_, np_);
+      const int m_blk = mp_ * p.cm + ci;
+      const int n_blk = np_ * p.cn + cj;
       long long row;
       bool valid;
       int sample;
@@ -516,6 +534,12 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   p.n_tiles = (int)((d->N + p.block_n - 1) / p.block_n);
   p.m_super = (p.m_tiles + p.cm - 1) / p.cm;
   p.n_super = (p.n_tiles + p.cn - 1) / p.cn;
+  {
+    static int env_gm = -1;
+    if (env_gm < 0) { const char* e = getenv("FD_GEMM_GROUP_M"); env_gm = e ? atoi(e) : 0; }
+    p.group_m = env_gm > 0 ? env_gm : 12;
+    if (p.group_m > p.m_super) p.group_m = p.m_super;
+  }
   // A part geometry (1/cn of the 128-row tile per CTA of a tile row)
   int a_box_rows = kBlockM / p.cn, a_bw = p.bw, a_bh = p.bh;
   if (p.mode != 0 && p.cn == 2) {

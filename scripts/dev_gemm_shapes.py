@@ -12,7 +12,7 @@ cfg = arch.SDXL_UNET_CONFIG
 unet = fd.UNet2DConditionModel(**cfg); unet.load_state_dict(arch.random_state_dict(arch.unet_param_shapes(cfg)))
 ehs = torch.randn(2, 77, 2048, device="cuda").to(BF)
 kv, lk = unet.text_kv(ehs)
-ts = TileStepGraph(unet, kv, lk, nb, 128, 128, BF, True, use_graph=True)
+ts = TileStepGraph(unet, kv, lk, [i // 2 for i in range(2 * nb)], [i % 2 for i in range(2 * nb)], 128, 128, BF, True, use_graph=True)
 ts.scaled.normal_(); ts.cond.normal_(); ts.temb.normal_()
 for _ in range(3): ts.graph.replay()
 torch.cuda.synchronize()

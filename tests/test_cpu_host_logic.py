@@ -144,3 +144,24 @@ def test_arch_key_layout_matches_oracle_and_known_counts():
         t.load_additional_layers(channel=64, encoder_kwargs=O.TINY_ENCODER_CONFIG)
     assert arch.unet_param_shapes(O.TINY_UNET_CONFIG, lq_channels=64, encoder_channels=(32, 64, 64, 64)) == \
         {k: tuple(p.shape) for k, p in t.state_dict().items()}
+
+
+def test_check_image_size_matches_oracle():
+    from PIL import Image
+    from faithdiff_dev_b200 import check_image_size
+    from oracle import faithdiff_oracle as O
+    for (w, h) in [(50, 37), (64, 64), (1, 1), (3840, 2160), (123, 8)]:
+        img = Image.fromarray(np.random.default_rng(w).integers(0, 256, (h, w, 3), dtype=np.uint8))
+        a, b = check_image_size(img), O.check_image_size(img)
+        assert a[1:] == b[1:] and np.array_equal(np.asarray(a[0]), np.asarray(b[0]))
+        assert a[3] % 8 == 0 and a[4] % 8 == 0
+
+
+def test_quantize_8bit_state_dict():
+    """utils/system.py:13-32 semantics: UNet tensors rounded through e4m3 (unscaled), the LQ Encoder untouched."""
+    from faithdiff_dev_b200 import quantize_8bit_state_dict
+    sd = {"conv_in.weight": torch.randn(8, 4, 3, 3) * 0.1, "denoise_encoder.conv_in.weight": torch.randn(8, 3, 3, 3)}
+    q = quantize_8bit_state_dict(sd)
+    assert torch.equal(q["denoise_encoder.conv_in.weight"], sd["denoise_encoder.conv_in.weight"])
+    ref = sd["conv_in.weight"].to(torch.float8_e4m3fn).float()
+    assert torch.equal(q["conv_in.weight"], ref) and not torch.equal(ref, sd["conv_in.weight"])

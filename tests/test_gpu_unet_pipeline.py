@@ -185,3 +185,37 @@ def test_pipeline_call_matches_oracle(models):
     for e in (ora.denoise_encoder, unet.denoise_encoder):
         e.tile_sample_min_size, e.tile_latent_min_size, e.use_tiling = 1024, 128, False
     vae_o.disable_tiling(); vae.disable_tiling()
+
+
+def test_factory_loads_reference_layout_checkpoints(tmp_path, models):
+    """FaithDiff_pipeline (create_FaithDiff_model.py:11-37): SDXL-layout UNet safetensors + VAE safetensors + FaithDiff.bin
+    pickle, written here from the oracle's state dicts, load through the factory and reproduce the directly-loaded UNet;
+    the fp8 option changes the weights exactly as quantize_8bit does."""
+    from safetensors.torch import save_file
+    fd, cfg, ora, unet, vae_o, vae = models
+    sd = {k: v.contiguous() for k, v in ora.state_dict().items()}
+    extra = ("denoise_encoder.", "information_transformer_layes.", "condition_embedding.", "spatial_ch_projs.")
+    os_unet = tmp_path / "sdxl" / "unet"
+    os_unet.mkdir(parents=True)
+    save_file({k: v for k, v in sd.items() if not k.startswith(extra)}, str(os_unet / "diffusion_pytorch_model.fp16.safetensors"))
+    (tmp_path / "vae").mkdir()
+    save_file({k: v.contiguous() for k, v in vae_o.state_dict().items()}, str(tmp_path / "vae" / "diffusion_pytorch_model.safetensors"))
+    torch.save(sd, str(tmp_path / "FaithDiff.bin"))
+    pipe = fd.FaithDiff_pipeline(str(tmp_path / "sdxl"), str(tmp_path / "vae"), str(tmp_path / "FaithDiff.bin"), unet_config=cfg,
+                                 vae_config=O.TINY_VAE_CONFIG)
+    x, lq, ehs, te, ids = _inputs(cfg, 16, 16)
+    kw = dict(encoder_hidden_states=ehs.cuda().to(BF), input_embedding=lq.cuda().to(BF),
+              added_cond_kwargs={"text_embeds": te.cuda().to(BF), "time_ids": ids.cuda()}, return_dict=False)
+    a = pipe.unet(x.cuda().to(BF), torch.tensor(951.), **kw)[0]
+    b = unet(x.cuda().to(BF), torch.tensor(951.), **kw)[0]
+    assert torch.equal(a, b)
+    pipe8 = fd.FaithDiff_pipeline(str(tmp_path / "sdxl"), str(tmp_path / "vae"), str(tmp_path / "FaithDiff.bin"), use_fp8=True,
+                                  unet_config=cfg, vae_config=O.TINY_VAE_CONFIG)
+    import copy
+    ora8 = copy.deepcopy(ora)
+    ora8.load_state_dict(fd.quantize_8bit_state_dict(sd))
+    with torch.no_grad():
+        ref8 = ora8(x.to(BF).float(), torch.tensor(951.), encoder_hidden_states=ehs.to(BF).float(), input_embedding=lq.to(BF).float(),
+                    added_cond_kwargs={"text_embeds": te.to(BF).float(), "time_ids": ids}, return_dict=False)[0]
+    c = pipe8.unet(x.cuda().to(BF), torch.tensor(951.), **kw)[0]
+    assert rel(c, ref8) < 2e-2 and rel(c, b) > 1e-2          # fp8-rounded weights: matches the fp8 oracle, differs from bf16
