@@ -1,6 +1,7 @@
 // Library-level plumbing: error string, launch counter, SM count, TMA descriptor encoding.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "../../include/faithdiff_b200.h"
@@ -14,6 +15,12 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("FD_PDL"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
 }
 
 int num_sms() {

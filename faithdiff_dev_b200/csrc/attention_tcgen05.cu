@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  pdl_launch_dependents();
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -245,7 +247,7 @@ extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64
     attr = true;
   }
   dim3 grid((lq + kQ - 1) / kQ, heads, batch);
-  attention_d64_kernel<<<grid, 192, smem_bytes, stream>>>(p);
+  FD_CHECK_CUDA(launch_pdl(attention_d64_kernel, grid, dim3(192), smem_bytes, stream, 1, p));
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

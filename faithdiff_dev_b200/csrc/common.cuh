@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <utility>
 
 namespace fd {
 
@@ -28,12 +30,44 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 int num_sms();
+bool pdl_enabled();   // FD_PDL=1 enables programmatic dependent launch (measured: no gain inside CUDA graphs -> default off)
+
+#ifdef __CUDACC__
+// Launch helper: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (and an optional cluster size).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency).
 int encode_tensor_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, CUtensorMapDataType dtype, CUtensorMapSwizzle swz);
 
 // ------------------------------------------------------------------ device PTX wrappers
 #ifdef __CUDACC__
+// Programmatic dependent launch: a kernel launched with the PDL attribute may start while its predecessor drains; everything
+// before pdl_wait() (barrier init, TMEM alloc, descriptor prefetch) overlaps the predecessor's tail.  pdl_wait() blocks until
+// the predecessor grid has completed and its memory is visible — no global memory may be touched before it.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ bool elect_one() {

@@ -109,6 +109,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
   if (csize > 1) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_launch_dependents();     // the next kernel may begin its own prologue on SMs this grid no longer needs
+  pdl_wait();                  // ... and this one touches global memory only after its predecessor has fully completed
 
   const int num_super = p.m_super * p.n_super;
   const int num_clusters = gridDim.x / csize;
@@ -608,23 +610,13 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   const int num_super = p.m_super * p.n_super;
   if (csize == 1) {
     const int grid = num_super < sms ? num_super : sms;
-    gemm_tcgen05_kernel<false><<<grid, kThreads, smem_bytes, stream>>>(p);
+    FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), smem_bytes, stream, 1, p));
   } else {
     const int maxc = max_clusters_for(csize);
     FD_REQUIRE(maxc > 0, "fd_gemm: no co-resident clusters of %d CTAs available", csize);
     const int clusters = num_super < maxc ? num_super : maxc;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(clusters * csize);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (p.pair) FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p));
-    else FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p));
+    if (p.pair) FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<true>, dim3(clusters * csize), dim3(kThreads), smem_bytes, stream, csize, p));
+    else FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<false>, dim3(clusters * csize), dim3(kThreads), smem_bytes, stream, csize, p));
   }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());

@@ -30,6 +30,8 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 __global__ void gn_partial_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1,
                                   int c1, long long hw, int groups, int R, float* __restrict__ partial) {
   extern __shared__ float sm[];
+  pdl_launch_dependents();
+  pdl_wait();
   const int ct = c0 + c1, V = ct >> 3;
   const int v = threadIdx.x % V, r = threadIdx.x / V;
   const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -72,6 +74,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk
                                    float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift) {
   __shared__ float s_mean[64], s_rstd[64];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int cpg = ct / groups;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -108,6 +112,8 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, int nchunk
 __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1,
                                 long long hw, long long total_vec, const float* __restrict__ scale,
                                 const float* __restrict__ shift, int silu, __nv_bfloat16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ct = c0 + c1, V = ct >> 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
     const int v = (int)(i % V);
@@ -131,50 +137,73 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
   }
 }
 
-// one warp per row; cols <= 1280 (5 vectors of 8 per lane)
-__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long rows, int cols,
-                                 float eps) {
+// one warp per PAIR of rows (both rows' loads are issued before either reduction: twice the bytes in flight per warp);
+// cols <= 1280 (5 vectors of 8 per lane); single-pass sum / sum-of-squares in fp32 with a mean-shifted second moment
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                                                        long long rows, int cols, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
-  const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (row >= rows) return;
+  const long long pair = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long row0 = pair * 2;
+  if (row0 >= rows) return;
+  const bool has1 = row0 + 1 < rows;
   const int V = cols >> 3;
-  float f[5][8];
-  float s = 0.f;
+  float f[2][NV][8];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < V && (r == 0 || has1)) load8(x + (row0 + r) * cols + v * 8, f[r][i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[r][i][j] = 0.f;
+      }
+    }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0 += f[0][i][j]; s1 += f[1][i][j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  const float m0 = s0 / cols, m1 = s1 / cols;
+  float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < V) {
-      load8(x + row * cols + v * 8, f[i]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[i][j];
+      for (int j = 0; j < 8; ++j) {
+        const float d0 = f[0][i][j] - m0, d1 = f[1][i][j] - m1;
+        q0 += d0 * d0; q1 += d1 * d1;
+      }
     }
   }
-  const float mean = warp_sum(s) / cols;
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < 5; ++i) {
-    const int v = lane + 32 * i;
-    if (v < V) {
+  for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+  const float rs0 = rsqrtf(q0 / cols + eps), rs1 = rsqrtf(q1 / cols + eps);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / cols + eps);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
     if (v < V) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      float o[8];
-      o[0] = (f[i][0] - mean) * rstd * g0.x + b0.x; o[1] = (f[i][1] - mean) * rstd * g0.y + b0.y;
-      o[2] = (f[i][2] - mean) * rstd * g0.z + b0.z; o[3] = (f[i][3] - mean) * rstd * g0.w + b0.w;
-      o[4] = (f[i][4] - mean) * rstd * g1.x + b1.x; o[5] = (f[i][5] - mean) * rstd * g1.y + b1.y;
-      o[6] = (f[i][6] - mean) * rstd * g1.z + b1.z; o[7] = (f[i][7] - mean) * rstd * g1.w + b1.w;
-      store8(out + row * cols + v * 8, o);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o0[8], o1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o0[j] = (f[0][i][j] - m0) * rs0 * gg[j] + bb[j];
+        o1[j] = (f[1][i][j] - m1) * rs1 * gg[j] + bb[j];
+      }
+      store8(out + row0 * cols + v * 8, o0);
+      if (has1) store8(out + (row0 + 1) * cols + v * 8, o1);
     }
   }
 }
@@ -207,15 +236,17 @@ extern "C" int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int
   float* shift = scale + (int64_t)batch * ct;
   const size_t smem = (size_t)2 * R * ct * sizeof(float);
   FD_REQUIRE(smem <= 48 * 1024, "fd_groupnorm_nhwc: smem %zu too large", smem);
-  gn_partial_kernel<<<dim3(nchunks, batch), V * R, smem, stream>>>((const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1,
-                                                                    c1, hw, groups, R, partial);
-  gn_finalize_kernel<<<batch, 1024, 0, stream>>>(partial, nchunks, groups, ct, hw, eps, gamma, beta, scale, shift);
+  FD_CHECK_CUDA(launch_pdl(gn_partial_kernel, dim3(nchunks, batch), dim3(V * R), smem, stream, 1, (const __nv_bfloat16*)x0, c0,
+                           (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, partial));
+  FD_CHECK_CUDA(launch_pdl(gn_finalize_kernel, dim3(batch), dim3(1024), 0, stream, 1, (const float*)partial, nchunks, groups, ct,
+                           (long long)hw, eps, gamma, beta, scale, shift));
   const long long total_vec = (long long)batch * hw * V;
   long long blocks = (total_vec + 255) / 256;
   const long long cap = (long long)num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  gn_apply_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, hw,
-                                                       total_vec, scale, shift, silu, (__nv_bfloat16*)out);
+  FD_CHECK_CUDA(launch_pdl(gn_apply_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, (const __nv_bfloat16*)x0, c0,
+                           (const __nv_bfloat16*)x1, c1, (long long)hw, total_vec, (const float*)scale, (const float*)shift, (int)silu,
+                           (__nv_bfloat16*)out));
   g_launches += 3;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -227,9 +258,12 @@ extern "C" int fd_layernorm(const void* x, const float* gamma, const float* beta
   FD_REQUIRE(x && out && gamma && beta, "fd_layernorm: null pointer");
   FD_REQUIRE(cols % 8 == 0 && cols <= 1280, "fd_layernorm: cols %d unsupported (need %%8==0 and <= 1280)", cols);
   const int threads = 256;
-  const long long blocks = (rows * 32 + threads - 1) / threads;
-  layernorm_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)out, rows,
-                                                             cols, eps);
+  const long long pairs = (rows + 1) / 2;
+  const long long blocks = (pairs * 32 + threads - 1) / threads;
+  const int nv = (cols / 8 + 31) / 32;
+#define FD_LN(NV) FD_CHECK_CUDA(launch_pdl(layernorm_kernel<NV>, dim3((unsigned)blocks), dim3(threads), 0, stream, 1, (const __nv_bfloat16*)x, gamma, beta, (__nv_bfloat16*)out, (long long)rows, cols, eps))
+  if (nv <= 1) FD_LN(1); else if (nv == 2) FD_LN(2); else if (nv == 3) FD_LN(3); else if (nv == 4) FD_LN(4); else FD_LN(5);
+#undef FD_LN
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -35,7 +35,7 @@ class EulerDiscreteScheduler:
         ratio = n // num_inference_steps
         ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.float32)
         ts += self.config.steps_offset
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         sig = np.concatenate([sig, [0.0]]).astype(np.float32)
         self.sigmas = torch.from_numpy(sig).to(torch.float32)          # kept on the host, like the reference
