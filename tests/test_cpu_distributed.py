@@ -29,7 +29,7 @@ def _worker(rank, world, port, q):
     for (i, j) in idx:
         cnt[0, :, i:i + k1, j:j + k2] += wts
     exchange_canvas(num)
-    q.put((rank, (num / cnt)))
+    q.put((rank, (num / cnt).numpy()))          # numpy: plain pickling, no shared-memory handle that can outlive the worker
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -43,7 +43,7 @@ def test_two_rank_canvas_exchange_matches_single_process_blend():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=240) for _ in range(2))
+    res = {r: torch.from_numpy(a) for r, a in (q.get(timeout=240) for _ in range(2))}
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
