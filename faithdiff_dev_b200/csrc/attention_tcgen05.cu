@@ -6,6 +6,7 @@
 //                                 O_j = P·V  (M128 N64 K128, A=P K-major from smem, B=V MN-major) -> TMEM cols [128,192)
 //   warps 2..5    : softmax/epilogue — one query row per thread: TMEM->regs, online max/sum in fp32 (exp2),
 //                   P (bf16) written to swizzled smem, running O kept in registers and rescaled each block.
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/faithdiff_b200.h"
 
@@ -114,57 +115,64 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
       tc_fence_after();
       const int kv0 = j * kKV;
       const bool full = kv0 + kKV <= p.lk;               // only the last block can need masking
-      // pass 1: row max (3-input max halves the instruction count)
+      // The block is either completely inside the key range (the common case: no index arithmetic at all) or the last,
+      // partially masked one; `full` is warp-uniform, so the two variants are separate code paths rather than selects.
       float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + c * 32, v);
-        tmem_ld_wait();
-        if (full) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float alpha = fast_exp2((m - mx) * p.scale_log2);
-      const float nmxs = -mx * p.scale_log2;
-      const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
+      float alpha, nmxs;
       uint64_t lsum2 = 0ull;
-      // pass 2: p = exp2(s*scale - max*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
+      auto softmax_block = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        // pass 1: row max (3-input max halves the instruction count)
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + c * 32, v);
-        tmem_ld_wait();
-        float e[32];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          tmem_ld_wait();
+          if constexpr (kFull) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scale2, nmxs2);
-          float a0, a1;
-          unpack_f2(t, a0, a1);
-          a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower: the loop is
-          a1 = fast_exp2(a1);      //  issue-bound, not MUFU-bound, and the extra converts cost more than they save)
-          if (!full) {
-            if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
-            if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
+            for (int i = 0; i < 32; i += 2) mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kv0 + c * 32 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
           }
-          e[i] = a0; e[i + 1] = a1;
-          lsum2 = add_f2(lsum2, pack_f2(a0, a1));
         }
-        uint8_t* half_base = prow + (c >> 1) * kTile;
+        alpha = fast_exp2((m - mx) * p.scale_log2);
+        nmxs = -mx * p.scale_log2;
+        const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
+        // pass 2: p = exp2(s*scale - max*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_lane + c * 32, v);
+          tmem_ld_wait();
+          float e[32];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int chunk = (c & 1) * 4 + g;
-          uint4 u;
-          u.x = pack_bf16(e[g * 8 + 0], e[g * 8 + 1]); u.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
-          u.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]); u.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
-          *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
+          for (int i = 0; i < 32; i += 2) {
+            const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scale2, nmxs2);
+            float a0, a1;
+            unpack_f2(t, a0, a1);
+            a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower, twice: the extra
+            a1 = fast_exp2(a1);      //  converts cost more issue slots than the halved MUFU count saves)
+            if constexpr (!kFull) {
+              if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
+              if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
+            }
+            e[i] = a0; e[i + 1] = a1;
+            lsum2 = add_f2(lsum2, pack_f2(a0, a1));
+          }
+          uint8_t* half_base = prow + (c >> 1) * kTile;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int chunk = (c & 1) * 4 + g;
+            uint4 u;
+            u.x = pack_bf16(e[g * 8 + 0], e[g * 8 + 1]); u.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
+            u.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]); u.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
+            *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
+          }
         }
-      }
+      };
+      if (full) softmax_block(std::true_type{}); else softmax_block(std::false_type{});
       float ls0, ls1;
       unpack_f2(lsum2, ls0, ls1);
       l = l * alpha + (ls0 + ls1);
