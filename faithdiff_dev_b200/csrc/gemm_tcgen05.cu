@@ -19,6 +19,8 @@ extern int64_t g_launches;
 struct GemmKParams {
   CUtensorMap amap[4];
   CUtensorMap bmap;
+  CUtensorMap rmap;    // residual, box = one epilogue chunk (32 rows x 32 columns, SWIZZLE_64B)
+  CUtensorMap omap;    // output,   box = one epilogue chunk (32 rows x 32 columns; GEGLU: x 16 columns, SWIZZLE_32B)
   int mode;            // 0 gemm, 1 conv
   int M, N;
   int m_tiles, n_tiles, block_n, stages;
@@ -39,6 +41,8 @@ struct GemmKParams {
   long long ld_out;
   float alpha;
   int act, bias_along_m, out_fp32;
+  int tma_epi;         // 1: the epilogue moves residual and output through shared memory with TMA (bf16 output, 16 B aligned)
+  int slot_bytes;      // bytes of one epilogue staging slot (a 32-row chunk of the output)
 };
 
 constexpr int kBlockM = 128;
@@ -48,12 +52,15 @@ constexpr int kAccCols = 256;                        // TMEM columns per accumul
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 320;                        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 
-struct __align__(8) PipeBarriers {
+struct __align__(16) PipeBarriers {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[8][2];     // per epilogue warp and staging slot: residual chunk landed
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  float bias_s[8][128];        // per epilogue warp: the bias of the (up to four) 32-column chunks it owns in the current tile
 };
 
 // Grouped rasterisation of the linear (super-)tile index: consecutive indices walk down a band of `group_m` tile rows before
@@ -71,14 +78,15 @@ __device__ __forceinline__ void raster_tile(int st, int m_super, int n_super, in
 
 // kPair = true instantiates the cta_group::2 (CTA-pair, UMMA M=256) variant; a kernel containing cta_group::2
 // instructions can only be launched with an even cluster size, hence two instantiations.
-template <bool kPair>
+template <bool kPair, int kEpi>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b_tile_bytes = (kPair ? p.block_n / 2 : p.block_n) * kBlockK * 2;   // pair: each CTA holds half of B
   const int stage_bytes = kATileBytes + b_tile_bytes;
-  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* slots = smem + (size_t)p.stages * stage_bytes;          // 8 warps x 2 slots (1024-aligned: stage_bytes % 2048 == 0)
+  PipeBarriers* bars = reinterpret_cast<PipeBarriers*>(slots + ((kEpi != 0 || p.tma_epi) ? 16 * p.slot_bytes : 0));
 
   const int csize = p.cm * p.cn;
   uint32_t crank = 0;
@@ -91,6 +99,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.bmap);
     tma_prefetch_desc(&p.amap[0]);
+    if (kEpi != 0 || p.tma_epi) { tma_prefetch_desc(&p.omap); if (p.residual) tma_prefetch_desc(&p.rmap); }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&bars->full[s], 1);
       mbar_init(&bars->empty[s], kPair ? 1 : p.cm + p.cn - 1);   // every CTA that multicasts into this stage must see it freed
@@ -99,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], kPair ? 16 : 8);    // 8 epilogue warps (pair: leader collects both CTAs')
     }
+    for (int w = 0; w < 8; ++w) { mbar_init(&bars->res_full[w][0], 1); mbar_init(&bars->res_full[w][1], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -230,6 +240,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     const int chalf = (warp - 2) >> 2;              // the two warps of a quadrant alternate 32-column chunks
     const int row_in_tile = quad * 32 + lane;
     const int nchunks = p.block_n >> 5;
+    // kEpi != 0 fixes the flag combination at compile time (the generic epilogue is ~2400 SASS instructions per chunk with
+    // a taken branch around every unused option; the profile showed the epilogue warps stalled on instruction fetch)
+    const int act = kEpi == 1 ? 0 : (kEpi == 2 ? 2 : p.act);
+    const bool tma_epi = kEpi != 0 || p.tma_epi;
+    const bool bias_m_mode = kEpi == 0 && p.bias_along_m;
+    const bool has_res = kEpi != 2 && p.residual != nullptr;
+    const bool col_bias = p.bias && !bias_m_mode;
+    float* bias_w = bars->bias_s[warp - 2];
+    // TMA epilogue state: two staging slots per warp, used alternately by the running chunk sequence number `qseq`
+    uint8_t* slot0 = slots + (size_t)(warp - 2) * 2 * p.slot_bytes;
+    uint64_t* rbar = bars->res_full[warp - 2];
+    uint32_t qseq = 0;
+    const int wx = p.mode ? (quad * 32) % p.bw : 0, wy = p.mode ? (quad * 32) / p.bw : 0;   // conv: this warp's 32 rows inside the tile's pixel patch
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int st = cluster_id; st < num_super; st += num_clusters) {
@@ -240,23 +263,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
       long long row;
       bool valid;
       int sample;
+      int bx = 0, by = 0, bimg = 0;                 // conv: TMA box origin of this warp's rows
       if (p.mode == 0) {
         row = (long long)m_blk * kBlockM + row_in_tile;
         valid = row < p.M;
-        sample = p.rowbias ? (int)(row / p.rows_per_batch) : 0;
+        sample = (p.rowbias && valid) ? (int)(row / p.rows_per_batch) : 0;
       } else {
         const int img = m_blk / p.tiles_per_img;
         const int r = m_blk - img * p.tiles_per_img;
-        const int y = (r / p.tiles_x) * p.bh + row_in_tile / p.bw;
-        const int x = (r % p.tiles_x) * p.bw + row_in_tile % p.bw;
+        const int ty = (r / p.tiles_x) * p.bh, tx = (r % p.tiles_x) * p.bw;
+        const int y = ty + row_in_tile / p.bw;
+        const int x = tx + row_in_tile % p.bw;
         valid = (img < p.batch) && (y < p.out_h) && (x < p.out_w);
         row = ((long long)img * p.out_h + y) * p.out_w + x;
-        sample = img;
+        sample = valid ? img : 0;
+        bx = tx + wx; by = ty + wy; bimg = img;
       }
       const int ncol0 = n_blk * p.block_n;
-      // residual rows are prefetched two 32-column chunks ahead (first two before the accumulator is even ready):
-      // each thread owns one output row, so these are long-latency L2 reads that must not sit on the critical path
-      const __nv_bfloat16* res_row = (p.residual && valid) ? p.residual + row * p.ld_res : nullptr;
+      const int box_row0 = m_blk * kBlockM + quad * 32;   // gemm mode: first of this warp's 32 rows
+
+      // ---- residual prefetch (two chunks ahead; the first two are requested before the accumulator is even ready)
+      //  TMA path:    one 32x32 box per chunk into the staging slot the result will later be stored from
+      //  direct path: each thread reads its own row (16 B per load) into registers
+      auto issue_res_load = [&](int c, uint32_t q) {           // one lane
+        uint64_t* bar = &rbar[q & 1];
+        uint8_t* dst = slot0 + (q & 1) * p.slot_bytes;
+        mbar_arrive_expect_tx(bar, 2048);
+        if (p.mode == 0) tma_load_2d(&p.rmap, bar, dst, ncol0 + c * 32, box_row0);
+        else tma_load_4d(&p.rmap, bar, dst, ncol0 + c * 32, bx, by, bimg);
+      };
+      const __nv_bfloat16* res_row = (!tma_epi && has_res && valid) ? p.residual + row * p.ld_res : nullptr;
       uint4 r0[4], r1[4];
       auto load_res = [&](int c, uint4 (&dst)[4]) {
 #pragma unroll
@@ -265,115 +301,217 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           dst[g8] = (res_row && n < p.N) ? __ldg(reinterpret_cast<const uint4*>(res_row + n)) : make_uint4(0u, 0u, 0u, 0u);
         }
       };
-      if (p.residual) {
-        if (chalf < nchunks) load_res(chalf, r0);
-        if (chalf + 2 < nchunks) load_res(chalf + 2, r1);
+      if (has_res) {
+        if (tma_epi) {
+          if (lane == 0) {
+            bulk_wait_read<0>();                    // my earlier stores have finished reading both slots
+            if (chalf < nchunks && ncol0 + chalf * 32 < p.N) issue_res_load(chalf, qseq);
+            if (chalf + 2 < nchunks && ncol0 + (chalf + 2) * 32 < p.N) issue_res_load(chalf + 2, qseq + 1);
+          }
+        } else {
+          if (chalf < nchunks) load_res(chalf, r0);
+          if (chalf + 2 < nchunks) load_res(chalf + 2, r1);
+        }
+      }
+      // Column bias: one coalesced read per chunk into this warp's shared-memory strip while the accumulator is still being
+      // computed; the per-chunk code then takes it with broadcast LDS.128.  (Read with LDG inside the chunk loop, the eight
+      // dependent L1/L2 round trips per chunk cost 6-10 us per GEMM.)
+      if (col_bias) {
+        __syncwarp();
+        int k = 0;
+        for (int c = chalf; c < nchunks; c += 2, ++k) {
+          const int n = ncol0 + c * 32 + lane;
+          bias_w[k * 32 + lane] = n < p.N ? __ldg(p.bias + n) : 0.f;
+        }
+        __syncwarp();
       }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccCols;
-      const float bias_m = (p.bias && p.bias_along_m && valid) ? p.bias[row] : 0.f;
+      const float bias_m = (bias_m_mode && p.bias && valid) ? p.bias[row] : 0.f;
+      const float* rb_row = (kEpi != 2 && p.rowbias) ? p.rowbias + (long long)sample * p.ld_rowbias : nullptr;
 
-      auto process = [&](int c, const uint4 (&res)[4]) {
-        uint32_t v[32];
-        tmem_ld32(t_row + c * 32, v);
-        tmem_ld_wait();
-        const int n0 = ncol0 + c * 32;
-        if (!valid || n0 >= p.N) return;
-        if (p.act == 2) {
-          // GEGLU: columns interleaved (h, g) -> 16 outputs
-          const int o0 = n0 >> 1;
-          float o[16];
+      // alpha, bias, per-sample row bias and activation on 8 consecutive columns n..n+7 (group g8 of the chunk)
+      auto affine_act8 = [&](float (&x)[8], const uint32_t* v8, const float* bs8, int n) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = n0 + 2 * j;
-            float h = __uint_as_float(v[2 * j]) * p.alpha;
-            float g = __uint_as_float(v[2 * j + 1]) * p.alpha;
-            if (n < p.N) {
-              if (p.bias) { h += __ldg(p.bias + n); g += __ldg(p.bias + n + 1); }
-            }
-            o[j] = h * gelu_erf_f(g);
-          }
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + o0;
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v8[j]) * p.alpha;
+        if (p.bias) {
+          if (bias_m_mode) {
 #pragma unroll
-          for (int g8 = 0; g8 < 2; ++g8) {
-            if (n0 + g8 * 16 >= p.N) break;
-            uint4 stv;
-            stv.x = pack_bf16(o[g8 * 8 + 0], o[g8 * 8 + 1]);
-            stv.y = pack_bf16(o[g8 * 8 + 2], o[g8 * 8 + 3]);
-            stv.z = pack_bf16(o[g8 * 8 + 4], o[g8 * 8 + 5]);
-            stv.w = pack_bf16(o[g8 * 8 + 6], o[g8 * 8 + 7]);
-            *reinterpret_cast<uint4*>(op + g8 * 8) = stv;
-          }
-          return;
-        }
-#pragma unroll
-        for (int g8 = 0; g8 < 4; ++g8) {
-          const int n = n0 + g8 * 8;
-          if (n >= p.N) break;
-          float x[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v[g8 * 8 + j]) * p.alpha;
-          if (p.bias) {
-            if (p.bias_along_m) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) x[j] += bias_m;
-            } else {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-              x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-              x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-            }
-          }
-          if (p.rowbias) {
-            const float* rb = p.rowbias + (long long)sample * p.ld_rowbias + n;
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb + 4));
+            for (int j = 0; j < 8; ++j) x[j] += bias_m;
+          } else {
+            const float4 b0 = *reinterpret_cast<const float4*>(bs8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bs8 + 4);
             x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
             x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
           }
-          if (p.act == 1) {
+        }
+        if (rb_row) {
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(rb_row + n));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(rb_row + n + 4));
+          x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
+          x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
+        }
+        if (act == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
-          } else if (p.act == 3) {
+          for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+        } else if (act == 3) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) x[j] = quick_gelu_f(x[j]);
-          }
-          if (p.residual) {
-            float2 f;
-            f = unpack_bf16(res[g8].x); x[0] += f.x; x[1] += f.y;
-            f = unpack_bf16(res[g8].y); x[2] += f.x; x[3] += f.y;
-            f = unpack_bf16(res[g8].z); x[4] += f.x; x[5] += f.y;
-            f = unpack_bf16(res[g8].w); x[6] += f.x; x[7] += f.y;
-          }
-          if (p.out_fp32) {
-            float* op = reinterpret_cast<float*>(p.out) + row * p.ld_out + n;
-            *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
-            *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
-          } else {
-            uint4 stv;
-            stv.x = pack_bf16(x[0], x[1]); stv.y = pack_bf16(x[2], x[3]);
-            stv.z = pack_bf16(x[4], x[5]); stv.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n) = stv;
-          }
+          for (int j = 0; j < 8; ++j) x[j] = quick_gelu_f(x[j]);
         }
       };
-      for (int c = chalf; c < nchunks; c += 4) {
-        process(c, r0);
-        if (p.residual && c + 4 < nchunks) load_res(c + 4, r0);
-        if (c + 2 < nchunks) {
-          process(c + 2, r1);
-          if (p.residual && c + 6 < nchunks) load_res(c + 6, r1);
+      // GEGLU: the chunk's columns are interleaved (h, g) pairs -> 16 outputs h * gelu(g)
+      auto geglu16 = [&](float (&o)[16], const uint32_t (&v)[32], const float* bs) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float h = __uint_as_float(v[2 * j]) * p.alpha;
+          float g = __uint_as_float(v[2 * j + 1]) * p.alpha;
+          if (col_bias) {
+            const float2 b = *reinterpret_cast<const float2*>(bs + 2 * j);
+            h += b.x; g += b.y;
+          }
+          o[j] = h * gelu_erf_f(g);
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
-        else mbar_arrive(&bars->tmem_empty[acc]);
+      };
+      auto release_acc = [&]() {                    // all of this warp's TMEM reads of the tile are done
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (kPair && crank != 0) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->tmem_empty[acc]), 0));
+          else mbar_arrive(&bars->tmem_empty[acc]);
+        }
+      };
+
+      if (tma_epi) {
+        // ---------------------------------------------------------------- TMA epilogue
+        // Every thread owns one output row.  Written straight to global memory that is 32 different 128-byte lines per
+        // warp instruction, and the LSU's one-line-per-cycle pace made the epilogue (not the MMA) the bound of every
+        // GEMM here.  Instead the row's 64-byte piece goes to a swizzled (conflict-free) staging slot and one TMA store
+        // per chunk writes the 32x32 box as full sectors; the residual comes in the same way, into the same slot.
+        const uint32_t sw64 = (uint32_t)((lane >> 1) & 3), sw32 = (uint32_t)((lane >> 2) & 1);
+        for (int c = chalf; c < nchunks; c += 2) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          if (c + 2 >= nchunks || n0 + 64 >= p.N) release_acc();
+          uint8_t* slot = slot0 + (qseq & 1) * p.slot_bytes;
+          if (has_res) {
+            mbar_wait(&rbar[qseq & 1], (qseq >> 1) & 1);
+          } else {
+            if (lane == 0) bulk_wait_read<1>();     // the store issued from this slot two chunks ago has read it
+            __syncwarp();
+          }
+          const float* bs = bias_w + ((c - chalf) >> 1) * 32;
+          if (act == 2) {
+            float o[16];
+            geglu16(o, v, bs);
+            uint8_t* rowp = slot + lane * 32;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4 stv;
+              stv.x = pack_bf16(o[g * 8 + 0], o[g * 8 + 1]); stv.y = pack_bf16(o[g * 8 + 2], o[g * 8 + 3]);
+              stv.z = pack_bf16(o[g * 8 + 4], o[g * 8 + 5]); stv.w = pack_bf16(o[g * 8 + 6], o[g * 8 + 7]);
+              *reinterpret_cast<uint4*>(rowp + ((g ^ sw32) << 4)) = stv;
+            }
+          } else {
+            uint8_t* rowp = slot + lane * 64;
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float x[8];
+              affine_act8(x, v + g8 * 8, bs + g8 * 8, n0 + g8 * 8);
+              uint4* sp = reinterpret_cast<uint4*>(rowp + ((g8 ^ sw64) << 4));
+              if (has_res) {
+                const uint4 rv = *sp;
+                float2 f;
+                f = unpack_bf16(rv.x); x[0] += f.x; x[1] += f.y;
+                f = unpack_bf16(rv.y); x[2] += f.x; x[3] += f.y;
+                f = unpack_bf16(rv.z); x[4] += f.x; x[5] += f.y;
+                f = unpack_bf16(rv.w); x[6] += f.x; x[7] += f.y;
+              }
+              uint4 stv;
+              stv.x = pack_bf16(x[0], x[1]); stv.y = pack_bf16(x[2], x[3]);
+              stv.z = pack_bf16(x[4], x[5]); stv.w = pack_bf16(x[6], x[7]);
+              *sp = stv;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int oc = act == 2 ? (n0 >> 1) : n0;
+            if (p.mode == 0) tma_store_2d(&p.omap, slot, oc, box_row0);
+            else tma_store_4d(&p.omap, slot, oc, bx, by, bimg);
+            bulk_commit();
+            if (has_res && c + 4 < nchunks && n0 + 128 < p.N) {
+              bulk_wait_read<0>();                  // the slot is reused for the residual two chunks on
+              issue_res_load(c + 4, qseq + 2);
+            }
+          }
+          ++qseq;
+        }
+        if (chalf >= nchunks || ncol0 + chalf * 32 >= p.N) release_acc();   // this warp owned no chunk of the tile
+      } else if constexpr (kEpi == 0) {
+        // ---------------------------------------------------------------- direct epilogue (fp32 or unaligned output)
+        auto process = [&](int c, const uint4 (&res)[4]) {
+          uint32_t v[32];
+          tmem_ld32(t_row + c * 32, v);
+          tmem_ld_wait();
+          const int n0 = ncol0 + c * 32;
+          if (!valid || n0 >= p.N) return;
+          const float* bs = bias_w + ((c - chalf) >> 1) * 32;
+          if (act == 2) {
+            float o[16];
+            geglu16(o, v, bs);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + (n0 >> 1);
+#pragma unroll
+            for (int g8 = 0; g8 < 2; ++g8) {
+              if (n0 + g8 * 16 >= p.N) break;
+              uint4 stv;
+              stv.x = pack_bf16(o[g8 * 8 + 0], o[g8 * 8 + 1]); stv.y = pack_bf16(o[g8 * 8 + 2], o[g8 * 8 + 3]);
+              stv.z = pack_bf16(o[g8 * 8 + 4], o[g8 * 8 + 5]); stv.w = pack_bf16(o[g8 * 8 + 6], o[g8 * 8 + 7]);
+              *reinterpret_cast<uint4*>(op + g8 * 8) = stv;
+            }
+            return;
+          }
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const int n = n0 + g8 * 8;
+            if (n >= p.N) break;
+            float x[8];
+            affine_act8(x, v + g8 * 8, bs + g8 * 8, n);
+            if (p.residual) {
+              float2 f;
+              f = unpack_bf16(res[g8].x); x[0] += f.x; x[1] += f.y;
+              f = unpack_bf16(res[g8].y); x[2] += f.x; x[3] += f.y;
+              f = unpack_bf16(res[g8].z); x[4] += f.x; x[5] += f.y;
+              f = unpack_bf16(res[g8].w); x[6] += f.x; x[7] += f.y;
+            }
+            if (p.out_fp32) {
+              float* op = reinterpret_cast<float*>(p.out) + row * p.ld_out + n;
+              *reinterpret_cast<float4*>(op) = make_float4(x[0], x[1], x[2], x[3]);
+              *reinterpret_cast<float4*>(op + 4) = make_float4(x[4], x[5], x[6], x[7]);
+            } else {
+              uint4 stv;
+              stv.x = pack_bf16(x[0], x[1]); stv.y = pack_bf16(x[2], x[3]);
+              stv.z = pack_bf16(x[4], x[5]); stv.w = pack_bf16(x[6], x[7]);
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ld_out + n) = stv;
+            }
+          }
+        };
+        for (int c = chalf; c < nchunks; c += 4) {
+          process(c, r0);
+          if (p.residual && c + 4 < nchunks) load_res(c + 4, r0);
+          if (c + 2 < nchunks) {
+            process(c + 2, r1);
+            if (p.residual && c + 6 < nchunks) load_res(c + 6, r1);
+          }
+        }
+        release_acc();
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (tma_epi && lane == 0) bulk_wait<0>();     // all output boxes written before the CTA retires
   }
   tc_fence_before();
   if (csize > 1) cluster_sync(); else __syncthreads();   // no CTA may exit while peers can still multicast into it
@@ -395,8 +533,7 @@ static int max_clusters_for(int csize) {
   if (cache[csize] >= 0) return cache[csize];
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gemm_tcgen05_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr_set = true;
   }
   cudaLaunchConfig_t cfg;
@@ -409,7 +546,7 @@ static int max_clusters_for(int csize) {
   at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<false>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<false, 0>, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
   cache[csize] = n;
   return n;
 }
@@ -549,10 +686,20 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     else { a_bw = p.bw / 2; p.a_part_dy = 0; p.a_part_dx = a_bw; }
   }
   const int stage_bytes = kATileBytes + (p.pair ? p.block_n / 2 : p.block_n) * kBlockK * 2;
-  const int smem_budget = 227 * 1024 - (int)sizeof(PipeBarriers) - 64;
+  // TMA epilogue whenever the output (and residual) rows can be addressed by a tensor map: bf16, 16-byte aligned rows
+  p.tma_epi = !d->out_fp32 && ((uintptr_t)d->out % 16 == 0) && (d->ld_out % 8 == 0) &&
+              (!d->residual || (((uintptr_t)d->residual % 16 == 0) && (d->ld_res % 8 == 0) && d->act != 2));
+  {
+    static int env_direct = -1;
+    if (env_direct < 0) { const char* e = getenv("FD_GEMM_DIRECT_EPILOGUE"); env_direct = e ? atoi(e) : 0; }
+    if (env_direct) p.tma_epi = 0;
+  }
+  p.slot_bytes = d->act == 2 ? 1024 : 2048;
+  const int staging_bytes = p.tma_epi ? 16 * p.slot_bytes : 0;
+  const int smem_budget = 227 * 1024 - (int)sizeof(PipeBarriers) - 64 - staging_bytes;
   p.stages = smem_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  const size_t smem_bytes = (size_t)p.stages * stage_bytes + sizeof(PipeBarriers);
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + staging_bytes + sizeof(PipeBarriers);
 
   // tensor maps
   if (d->mode == 0) {
@@ -593,6 +740,30 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     if (encode_tensor_map(&p.bmap, d->b, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                           CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
   }
+  if (p.tma_epi) {
+    // one box = the 32 rows of an epilogue warp x one 32-column accumulator chunk (GEGLU: 16 output columns)
+    const int box_w = (d->mode == 0 || p.bw >= 32) ? 32 : p.bw, box_h = 32 / box_w;       // conv: the 32 rows as a pixel rectangle of the patch
+    for (int which = 0; which < 2; ++which) {
+      const void* base = which == 0 ? d->out : d->residual;
+      if (!base) continue;
+      const uint64_t ld = (uint64_t)(which == 0 ? d->ld_out : d->ld_res);
+      const uint64_t ncols = (uint64_t)((which == 0 && d->act == 2) ? d->N / 2 : d->N);
+      const uint32_t box_c = (which == 0 && d->act == 2) ? 16 : 32;
+      const CUtensorMapSwizzle sw = box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B;
+      CUtensorMap* map = which == 0 ? &p.omap : &p.rmap;
+      if (d->mode == 0) {
+        uint64_t dims[2] = {ncols, (uint64_t)M};
+        uint64_t str[1] = {ld * 2};
+        uint32_t box[2] = {box_c, 32};
+        if (encode_tensor_map(map, base, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, sw)) return 3;
+      } else {
+        uint64_t dims[4] = {ncols, (uint64_t)p.out_w, (uint64_t)p.out_h, (uint64_t)d->batch};
+        uint64_t str[3] = {ld * 2, ld * 2 * p.out_w, ld * 2 * p.out_w * p.out_h};
+        uint32_t box[4] = {box_c, (uint32_t)box_w, (uint32_t)box_h, 1};
+        if (encode_tensor_map(map, base, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, sw)) return 3;
+      }
+    }
+  }
   p.bias = d->bias; p.rowbias = d->rowbias; p.rows_per_batch = d->rows_per_batch > 0 ? d->rows_per_batch : M;
   p.ld_rowbias = d->ld_rowbias > 0 ? d->ld_rowbias : d->N;
   FD_REQUIRE(!d->rowbias || (((uintptr_t)d->rowbias % 16) == 0 && p.ld_rowbias % 4 == 0), "fd_gemm: rowbias alignment");
@@ -600,23 +771,37 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   p.out = d->out; p.ld_out = d->ld_out; p.alpha = d->alpha == 0.f ? 1.f : d->alpha;
   p.act = d->act; p.bias_along_m = d->bias_along_m; p.out_fp32 = d->out_fp32;
 
+  // epilogue specialisation: 1 = TMA epilogue, no activation (bias / per-sample bias / residual optional);
+  // 2 = TMA epilogue, GEGLU with column bias; 0 = generic (every option at run time, direct stores possible)
+  int epi = 0;
+  if (p.tma_epi && !p.pair && !d->bias_along_m) {
+    if (d->act == 0) epi = 1;
+    else if (d->act == 2 && !d->rowbias && !d->residual) epi = 2;
+  }
+  {
+    static int env_generic = -1;
+    if (env_generic < 0) { const char* e = getenv("FD_GEMM_GENERIC_EPILOGUE"); env_generic = e ? atoi(e) : 0; }
+    if (env_generic) epi = 0;
+  }
+  using KernelFn = void (*)(GemmKParams);
+  static const KernelFn kernels[4] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
+                                      gemm_tcgen05_kernel<true, 0>};
   static bool attr_set = false;
   if (!attr_set) {
-    FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 4; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int csize = p.cm * p.cn;
   const int num_super = p.m_super * p.n_super;
+  KernelFn kernel = p.pair ? kernels[3] : kernels[epi];
   if (csize == 1) {
     const int grid = num_super < sms ? num_super : sms;
-    FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<false>, dim3(grid), dim3(kThreads), smem_bytes, stream, 1, p));
+    FD_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, 1, p));
   } else {
     const int maxc = max_clusters_for(csize);
     FD_REQUIRE(maxc > 0, "fd_gemm: no co-resident clusters of %d CTAs available", csize);
     const int clusters = num_super < maxc ? num_super : maxc;
-    if (p.pair) FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<true>, dim3(clusters * csize), dim3(kThreads), smem_bytes, stream, csize, p));
-    else FD_CHECK_CUDA(launch_pdl(gemm_tcgen05_kernel<false>, dim3(clusters * csize), dim3(kThreads), smem_bytes, stream, csize, p));
+    FD_CHECK_CUDA(launch_pdl(kernel, dim3(clusters * csize), dim3(kThreads), smem_bytes, stream, csize, p));
   }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());

@@ -23,6 +23,7 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print("graph replay nb=%d: %.2f ms per replay = %.2f ms per tile (%.0f TF/s ref-alg)" % (nb, ms, ms / nb, 14.216 * nb / ms * 1e3), flush=True)
 rec = collections.defaultdict(list)
+order = []
 def wrap(name, flop):
     f = getattr(O, name)
     def g(*a, **k):
@@ -30,6 +31,7 @@ def wrap(name, flop):
         s.record(); r = f(*a, **k); e.record()
         shp = tuple(tuple(v.shape) for v in a[:2] if torch.is_tensor(v))
         rec[(name, shp, k.get("act", 0), k.get("stride", 1), k.get("residual") is not None)].append((s, e, flop(a, k, r)))
+        order.append((name, shp, k.get('residual') is not None, (k.get('bias') is not None) or (len(a) > 2 and torch.is_tensor(a[2])), s, e))
         return r
     setattr(O, name, g)
 wrap("gemm", lambda a, k, r: 2.0 * a[0].shape[0] * a[1].shape[0] * a[1].shape[1])
@@ -51,3 +53,8 @@ for t, n, k, f in rows: cls[k[0]] += t
 print("instrumented total %.2f ms: " % tot + ", ".join("%s %.2f" % kv for kv in sorted(cls.items(), key=lambda kv: -kv[1])))
 for t, n, k, f in rows[:45]:
     print("  %7.3f ms x%3d (%6.1f us each) %-9s %-46s act=%d s=%d res=%d %s" % (t, n, t / n * 1e3, k[0], str(k[1]), k[2], k[3], k[4], ("%.0f TF/s" % (f / t / 1e9)) if f else ""))
+
+if os.environ.get("FD_SEQ"):
+    lo, hi = [int(v) for v in os.environ["FD_SEQ"].split(",")]
+    for i, (name, shp, res, bias, s_, e_) in enumerate(order[lo:hi]):
+        print("  #%4d %-9s %-44s res=%d bias=%d %7.1f us" % (lo + i, name, str(shp), res, bias, s_.elapsed_time(e_) * 1e3))
