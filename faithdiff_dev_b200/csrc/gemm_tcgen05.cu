@@ -522,10 +522,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------- host side
-// Joint choice of the N tile and the cluster shape from a cycle model per 64-deep k-block:
-//   tensor pipe  2*bn cycles (4 MMAs of 128 x bn x 16 at 8192 FLOP/clk/SM)
-//   L2 -> SMEM   (16384/cn + 128*bn/cm) / 64 cycles (64 B/clk/SM)
-// times the number of waves of (super-)tiles over the co-resident clusters, plus per-tile epilogue/fixed cost.
+// Joint choice of the N tile and of single-CTA (128 x bn) versus CTA-pair (256 x bn, cta_group::2) tiles from a cycle
+// model, fitted to a sweep of every GEMM/conv shape of the SDXL UNet tile-step (scripts/dev_gemm_tune.py):
+//   per 64-deep k-block  max(tensor pipe 2*bn cycles, operand bytes into one SM / F)
+//                        bytes = 128*(128 + bn) single, 128*(128 + bn/2) pair (each CTA of a pair loads half of B);
+//                        F = 45 (single) / 35 (pair) B/clk/SM is what L2 delivers with all 148 SMs pulling — the UNet's
+//                        shapes are bound by this operand feed, not by the MMA, which is why the pair's halved B traffic wins
+//   per tile             2000 + 8*bn cycles (epilogue share that does not overlap), + 1500 for a pair (cluster hand-shakes)
+// times the number of waves of tiles over the 148 SMs / 74 pairs.
 struct TileChoice { int bn, cm, cn, pair; };
 static int max_clusters_for(int csize) {
   static int cache[5] = {-1, -1, -1, -1, -1};
@@ -550,25 +554,20 @@ static int max_clusters_for(int csize) {
   cache[csize] = n;
   return n;
 }
-// Joint choice of the N tile and of 1-CTA vs CTA-pair execution from a cycle model per 64-deep k-block:
-//   tensor pipe   2*bn cycles per SM (128 x bn x 64 MACs at 4096 MAC/clk/SM)
-//   SMEM ingest   (16384 + 128*bn) / 57 cycles for a 1-CTA tile, (16384 + 64*bn) / 57 for a pair (each CTA stages only
-//                 half of B) — ~57 B/clk/SM is what TMA delivers into one SM (measured; multicast does not raise it)
-// times the waves of tiles over the co-resident CTAs/pairs, plus a per-tile epilogue/fixed cost.
 static TileChoice pick_tiling(long long m_tiles, long long N, int num_kb, int sms, int force_pair) {
   TileChoice best = {32, 1, 1, 0};
   double best_cost = 1e30;
   for (int pair = 0; pair < 2; ++pair) {
-    if (pair != (force_pair > 0 ? 1 : 0)) continue;   // measured: the pair variant is not faster → opt-in only
+    if (force_pair >= 0 && pair != force_pair) continue;
     const int units = pair ? max_clusters_for(2) : sms;
     if (units <= 0) continue;
     for (int bn = 256; bn >= 32; bn -= 32) {
       const long long n_tiles = (N + bn - 1) / bn;
       const long long work = (pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
       const long long waves = (work + units - 1) / units;
-      // per-tile time ~ k-blocks x max(tensor pipe 2*bn cycles, smem-bandwidth floor) + epilogue/fixed cost (tuned on B200)
-      const double t_kb = fmax(2.0 * bn, 128.0 + bn);
-      const double cost = waves * (t_kb * num_kb + 20.0 * num_kb + 2000.0 + 10.0 * bn);
+      const double feed = 128.0 * (128.0 + (pair ? bn / 2 : bn)) / (pair ? 35.0 : 45.0);
+      const double t_kb = fmax(2.0 * bn, feed);
+      const double cost = waves * (t_kb * num_kb + 2000.0 + 8.0 * bn + (pair ? 1500.0 : 0.0));
       if (cost < best_cost - 1e-9) { best_cost = cost; best = {bn, pair ? 2 : 1, 1, pair}; }
     }
   }
@@ -661,13 +660,16 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     const char* pr = getenv("FD_GEMM_PAIR");             // 0 / 1 forces 1-CTA / CTA-pair tiles
     env_pair = pr ? atoi(pr) : -1;
   }
-  TileChoice tc = pick_tiling(p.m_tiles, d->N, p.taps * p.kb_per_tap, sms, env_pair);
+  int want_pair = env_pair;                               // -1 auto, 0 single CTA, 1 CTA pair
+  if (d->block_n & 0x1000) want_pair = 1;
+  if (d->block_n & 0x2000) want_pair = 0;
+  TileChoice tc = pick_tiling(p.m_tiles, d->N, p.taps * p.kb_per_tap, sms, want_pair);
   if (env_cm > 0 && env_cn > 0) {
     tc = pick_tiling(p.m_tiles, d->N, p.taps * p.kb_per_tap, sms, 0);
     tc.cm = env_cm; tc.cn = env_cn; tc.pair = 0;
   }
   if (env_bn > 0) tc.bn = env_bn;
-  if (d->block_n) tc.bn = d->block_n;
+  if (d->block_n & 0xfff) tc.bn = d->block_n & 0xfff;
   p.block_n = tc.bn; p.cm = tc.cm; p.cn = tc.cn; p.pair = tc.pair;
   FD_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= 256, "fd_gemm: bad block_n %d", p.block_n);
   p.n_tiles = (int)((d->N + p.block_n - 1) / p.block_n);
@@ -774,7 +776,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   // epilogue specialisation: 1 = TMA epilogue, no activation (bias / per-sample bias / residual optional);
   // 2 = TMA epilogue, GEGLU with column bias; 0 = generic (every option at run time, direct stores possible)
   int epi = 0;
-  if (p.tma_epi && !p.pair && !d->bias_along_m) {
+  if (p.tma_epi && !d->bias_along_m) {
     if (d->act == 0) epi = 1;
     else if (d->act == 2 && !d->rowbias && !d->residual) epi = 2;
   }
@@ -784,16 +786,16 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     if (env_generic) epi = 0;
   }
   using KernelFn = void (*)(GemmKParams);
-  static const KernelFn kernels[4] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
-                                      gemm_tcgen05_kernel<true, 0>};
+  static const KernelFn kernels[6] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
+                                      gemm_tcgen05_kernel<true, 0>,  gemm_tcgen05_kernel<true, 1>,  gemm_tcgen05_kernel<true, 2>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 4; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 6; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int csize = p.cm * p.cn;
   const int num_super = p.m_super * p.n_super;
-  KernelFn kernel = p.pair ? kernels[3] : kernels[epi];
+  KernelFn kernel = kernels[(p.pair ? 3 : 0) + epi];
   if (csize == 1) {
     const int grid = num_super < sms ? num_super : sms;
     FD_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, 1, p));

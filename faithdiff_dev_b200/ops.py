@@ -53,7 +53,7 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
     return out
 
 
-def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None):
+def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0):
     """3x3 conv on NHWC bf16 x [B,H,W,C] (optionally channel-concatenated with x2); w packed [N, 9*(C+C2)]."""
     assert x.dim() == 4 and x.dtype == BF16 and x.stride(3) == 1
     B, H, W, C0 = x.shape
@@ -84,7 +84,7 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(3) == 1
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(2)
-    d.out, d.ld_out, d.alpha = out.data_ptr(), out.stride(2), 1.0
+    d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(2), 1.0, block_n
     check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(conv)")
     return out
 

@@ -53,7 +53,8 @@ typedef struct fd_gemm_desc {
   void* out;             /* [M, ld_out]                                                                   */
   int64_t ld_out;
   float alpha;
-  int32_t block_n;       /* 0 = auto; else multiple of 32 in [32, 256]                                    */
+  int32_t block_n;       /* 0 = auto; low 12 bits: N tile, multiple of 32 in [32, 256]; tuning hooks: bit 12    */
+                         /* forces CTA-pair (cta_group::2) tiles, bit 13 forces single-CTA tiles               */
 } fd_gemm_desc;
 int fd_gemm(const fd_gemm_desc* d, void* stream);
 int fd_sizeof_gemm_desc(void);   /* lets a foreign-language binding verify its struct mirror */
