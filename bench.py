@@ -210,7 +210,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="4k")
-    ap.add_argument("--tiles-per-launch", type=int, default=4)
+    ap.add_argument("--tiles-per-launch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = workload(args.workload)

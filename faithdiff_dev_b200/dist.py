@@ -12,8 +12,8 @@ def shard_tiles(num_tiles, rank, world_size):
 
 
 # measured cost (ms) of one CUDA-graph replay of the UNet tile-step for n tiles per launch on B200 (profiles/): batching
-# amortises prologues and improves wave quantisation up to ~3 tiles
-REPLAY_COST_MS = {1: 27.4, 2: 41.1, 3: 57.8, 4: 79.3}
+# amortises prologues and improves wave quantisation (20.7 ms for a single tile, 15.8 ms per tile from 7 tiles up)
+REPLAY_COST_MS = {1: 20.73, 2: 35.80, 3: 48.70, 4: 64.75, 5: 79.83, 6: 95.50, 7: 110.47, 8: 126.53}
 
 
 def plan_launch_groups(my_tiles, sizes, costs=None):
@@ -49,17 +49,18 @@ def shard_units(num_tiles, rank, world_size):
     return list(range(lo, hi))
 
 
-# measured replay cost (ms) by number of SAMPLES (= units) per launch; odd sizes interpolated
-UNIT_REPLAY_COST_MS = {1: 18.0, 2: 27.4, 3: 34.5, 4: 41.1, 5: 49.5, 6: 57.8, 7: 68.5, 8: 79.3}
+# measured replay cost (ms) by number of SAMPLES (= units) per launch (9, 11, 13, 15 interpolated)
+UNIT_REPLAY_COST_MS = {1: 15.60, 2: 20.73, 3: 26.28, 4: 35.80, 5: 42.89, 6: 48.70, 7: 56.53, 8: 64.75, 9: 72.3, 10: 79.83,
+                       11: 87.7, 12: 95.50, 13: 103.0, 14: 110.47, 15: 118.5, 16: 126.53}
 
 
-def plan_unit_groups(units, max_samples=8):
+def plan_unit_groups(units, max_samples=16):
     """Split a contiguous unit range into consecutive launch groups minimising the summed replay cost."""
     n = len(units)
     best = [0.0] + [float("inf")] * n
     choice = [0] * (n + 1)
     for i in range(1, n + 1):
-        for sz in range(1, min(max_samples, i) + 1):
+        for sz in range(1, min(max_samples, i, max(UNIT_REPLAY_COST_MS)) + 1):
             c = best[i - sz] + UNIT_REPLAY_COST_MS[sz]
             if c < best[i] - 1e-9:
                 best[i], choice[i] = c, sz

@@ -107,7 +107,7 @@ class FaithDiffStableDiffusionXLPipeline:
         self.watermark = None
         self.device = torch.device("cuda")
         self.rank, self.world_size, self.process_group = 0, 1, None
-        self.tiles_per_launch = 4          # upper bound; the launch plan mixes group sizes 1..N by measured cost
+        self.tiles_per_launch = 8          # upper bound; the launch plan mixes group sizes 1..N by measured cost
         self.use_cuda_graph = True
         self._graphs = {}
 

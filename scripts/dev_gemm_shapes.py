@@ -12,7 +12,8 @@ cfg = arch.SDXL_UNET_CONFIG
 unet = fd.UNet2DConditionModel(**cfg); unet.load_state_dict(arch.random_state_dict(arch.unet_param_shapes(cfg)))
 ehs = torch.randn(2, 77, 2048, device="cuda").to(BF)
 kv, lk = unet.text_kv(ehs)
-ts = TileStepGraph(unet, kv, lk, [i // 2 for i in range(2 * nb)], [i % 2 for i in range(2 * nb)], 128, 128, BF, True, use_graph=True)
+ns = int(os.environ.get("FD_SAMPLES", 2 * nb))        # odd sample counts occur in the multi-GPU unit split
+ts = TileStepGraph(unet, kv, lk, [i // 2 for i in range(ns)], [i % 2 for i in range(ns)], 128, 128, BF, True, use_graph=True)
 ts.scaled.normal_(); ts.cond.normal_(); ts.temb.normal_()
 for _ in range(3): ts.graph.replay()
 torch.cuda.synchronize()
@@ -21,7 +22,9 @@ e0.record()
 for _ in range(10): ts.graph.replay()
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
-print("graph replay nb=%d: %.2f ms per replay = %.2f ms per tile (%.0f TF/s ref-alg)" % (nb, ms, ms / nb, 14.216 * nb / ms * 1e3), flush=True)
+nb = ns / 2
+print("graph replay samples=%d: %.2f ms per replay = %.2f ms per tile (%.0f TF/s ref-alg)" % (ns, ms, ms / nb, 14.216 * nb / ms * 1e3), flush=True)
+if os.environ.get("FD_REPLAY_ONLY"): sys.exit(0)
 rec = collections.defaultdict(list)
 order = []
 def wrap(name, flop):

@@ -68,5 +68,6 @@ def test_shard_and_launch_plan():
     for n in range(0, 40):
         g = plan_launch_groups(list(range(n)), [1, 2, 3, 4])
         assert [t for grp in g for t in grp] == list(range(n)) and all(1 <= len(x) <= 4 for x in g)
-    assert sorted(len(x) for x in plan_launch_groups(list(range(28)), [1, 2, 3, 4])) == [3] * 8 + [4]
+    assert sorted(len(x) for x in plan_launch_groups(list(range(28)), [1, 2, 3, 4])) == [4] * 7
+    assert sorted(len(x) for x in plan_launch_groups(list(range(28)), range(1, 9))) == [7] * 4
     assert sorted(len(x) for x in plan_launch_groups(list(range(7)), [1, 2, 3, 4])) == [3, 4]
