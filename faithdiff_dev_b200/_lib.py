@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfaithdiff_b200.so")
+# FAITHDIFF_B200_LIB: A/B-compare two builds of the library in one process launch each (development only)
+LIB_PATH = os.environ.get("FAITHDIFF_B200_LIB") or os.path.join(_HERE, "libfaithdiff_b200.so")
 
 
 class GemmDesc(C.Structure):

@@ -1,11 +1,15 @@
 // Flash-style attention for head_dim 64 on tcgen05 (sm_100a), bf16 in/out, fp32 softmax + accumulation.
-// One CTA = one (batch, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax overlaps the
-// other's MMAs.
-//   warp 0 lane 0 : TMA producer  (Q once; K/V 128-key blocks, 2-stage ring, 128B swizzle)
-//   warp 1 lane 0 : MMA issuer    S = Q·K^T  (M128 N128 K64, K-major A/B)  -> TMEM cols [0,128)
-//                                 O_j = P·V  (M128 N64 K128, A=P K-major from smem, B=V MN-major) -> TMEM cols [128,192)
-//   warps 2..5    : softmax/epilogue — one query row per thread: TMEM->regs, online max/sum in fp32 (exp2),
-//                   P (bf16) written to swizzled smem, running O kept in registers and rescaled each block.
+// One CTA = one (batch, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax overlaps the other's MMAs.
+//   warp 0 lane 0 : TMA producer  (Q once; K and V 128-key blocks in separate 2-stage rings, 128B swizzle.  K_j is released
+//                                 as soon as S_j = Q K_j^T has been computed, so K_{j+2} streams in two blocks ahead)
+//   warp 1 lane 0 : MMA issuer    S_{j+1} = Q K_{j+1}^T (M128 N128 K64) -> TMEM cols [0,128) is issued as soon as the softmax
+//                                 warps have copied S_j into registers, i.e. it runs under the exponentials of block j;
+//                                 O += P_j V_j (M128 N64 K128, A = P from smem, B = V MN-major) accumulates in TMEM cols [128,192)
+//   warps 2..5    : softmax — one query row per thread: the whole S row (128 fp32) is read from TMEM once, then max, exp2 and
+//                   row sum in registers; P (bf16) goes to swizzled smem.  The running output stays in TMEM; it is rescaled
+//                   in place only when some row's maximum grew by more than 2^8 since the maximum the row last committed to
+//                   (the softmax is exact for any reference value, and with p <= 2^8 bf16/fp32 keep their precision), so
+//                   the per-block "load O, rescale, add" of a register-resident accumulator is gone.
 #include <type_traits>
 #include "common.cuh"
 #include "../../include/faithdiff_b200.h"
@@ -23,9 +27,10 @@ struct AttnParams {
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
 constexpr int kTile = kQ * kD * 2;   // 16 KB
+constexpr float kRescaleThreshold = 8.f;   // log2 units
 
 struct __align__(8) AttnBars {
-  uint64_t q_full, kv_full[2], kv_empty[2], s_full, p_full, o_full;
+  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_read, p_full, o_done;
   uint32_t tmem_base;
 };
 
@@ -43,10 +48,14 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
     mbar_init(&bars->q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bars->kv_full[s], 1); mbar_init(&bars->kv_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->k_full[s], 1); mbar_init(&bars->k_empty[s], 1);
+      mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
+    }
     mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_read, 4);
     mbar_init(&bars->p_full, 4);
-    mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->o_done, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -64,12 +73,25 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     if (lane == 0) {
       mbar_arrive_expect_tx(&bars->q_full, kTile);
       tma_load_2d(&p.qmap, &bars->q_full, sQ, head * kD, b * p.lq + qblk * kQ);
-      for (int j = 0; j < nkv; ++j) {
+      auto load_k = [&](int j) {
         const int s = j & 1;
-        mbar_wait(&bars->kv_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTile);
-        tma_load_2d(&p.kmap, &bars->kv_full[s], sK + s * kTile, head * kD, b * p.lk + j * kKV);
-        tma_load_2d(&p.vmap, &bars->kv_full[s], sV + s * kTile, head * kD, b * p.lk + j * kKV);
+        mbar_wait(&bars->k_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->k_full[s], kTile);
+        tma_load_2d(&p.kmap, &bars->k_full[s], sK + s * kTile, head * kD, b * p.lk + j * kKV);
+      };
+      auto load_v = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&bars->v_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->v_full[s], kTile);
+        tma_load_2d(&p.vmap, &bars->v_full[s], sV + s * kTile, head * kD, b * p.lk + j * kKV);
+      };
+      // request order = order in which the slots become free: K_{j+1}'s slot (after S_{j-1}) before V_j's (after PV_{j-2})
+      load_k(0);
+      if (nkv > 1) load_k(1);
+      load_v(0);
+      for (int j = 1; j < nkv; ++j) {
+        if (j + 1 < nkv) load_k(j + 1);
+        load_v(j);
       }
     }
   } else if (warp == 1) {
@@ -77,79 +99,110 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
       const uint32_t idesc_s = umma_idesc(128, 128, 1, 0, 0);
       const uint32_t idesc_o = umma_idesc(128, 64, 1, 0, 1);   // B (=V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
-      mbar_wait(&bars->q_full, 0);
-      for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t aK = smem_u32(sK + s * kTile), aV = smem_u32(sV + s * kTile);
-        // S = Q K^T. (S_{j} may overwrite S_{j-1}: the softmax warps finished reading it before p_full(j-1).)
+      auto issue_s = [&](int j) {
+        const uint32_t aK = smem_u32(sK + (j & 1) * kTile);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
         tc_commit(&bars->s_full);
-        // O_j = P V once the softmax warps have published P_j
+        tc_commit(&bars->k_empty[j & 1]);
+      };
+      mbar_wait(&bars->q_full, 0);
+      mbar_wait(&bars->k_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {
+          // S_{j+1} overwrites S_j as soon as every softmax warp holds its S_j rows in registers
+          mbar_wait(&bars->k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(&bars->s_read, j & 1);
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        const int s = j & 1;
+        mbar_wait(&bars->v_full[s], (j >> 1) & 1);
         mbar_wait(&bars->p_full, j & 1);
         tc_fence_after();
+        const uint32_t aV = smem_u32(sV + s * kTile);
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_f16(tmem + 128, umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
-                   umma_desc_sw128(aV + k * 2048, 0, 1024), idesc_o, k != 0);
-        tc_commit(&bars->kv_empty[s]);
-        tc_commit(&bars->o_full);
+                   umma_desc_sw128(aV + k * 2048, 0, 1024), idesc_o, (j != 0) || (k != 0));
+        tc_commit(&bars->v_empty[s]);
+        tc_commit(&bars->o_done);
       }
     }
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                       // query row within the block
     const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    uint64_t o2[32];                                      // running output row, packed fp32x2
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o2[i] = 0ull;
-    float m = -INFINITY, l = 0.f;
+    float m_used = -INFINITY, l = 0.f;                    // reference maximum the row's P and O are expressed in; row sum
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
     const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(t_lane + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_read);          // the tensor core may now compute S_{j+1}
       const int kv0 = j * kKV;
-      const bool full = kv0 + kKV <= p.lk;               // only the last block can need masking
-      // The block is either completely inside the key range (the common case: no index arithmetic at all) or the last,
-      // partially masked one; `full` is warp-uniform, so the two variants are separate code paths rather than selects.
-      float mx = m;
-      float alpha, nmxs;
-      uint64_t lsum2 = 0ull;
-      auto softmax_block = [&](auto full_tag) {
-        constexpr bool kFull = decltype(full_tag)::value;
-        // pass 1: row max (3-input max halves the instruction count)
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + c * 32, v);
-          tmem_ld_wait();
-          if constexpr (kFull) {
+      const bool full = kv0 + kKV <= p.lk;               // only the last block can need masking (warp-uniform)
+      float mx = m_used;
+      if (full) {
+        // four independent 3-input-max chains (a single chain is 64 dependent instructions of latency)
+        float m1 = mx, m2 = mx, m3 = mx;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (kv0 + c * 32 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
+        for (int i = 0; i < 128; i += 8) {
+          mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+          m1 = max3_f(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          m2 = max3_f(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
+          m3 = max3_f(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
         }
-        alpha = fast_exp2((m - mx) * p.scale_log2);
-        nmxs = -mx * p.scale_log2;
-        const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
-        // pass 2: p = exp2(s*scale - max*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
+        mx = fmaxf(max3_f(mx, m1, m2), m3);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (kv0 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        mbar_wait(&bars->o_done, (j - 1) & 1);            // P_{j-1} V_{j-1} finished: sP may be rewritten, O may be rescaled
+        tc_fence_after();
+        const bool grew = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, grew)) {
+          const float alpha = fast_exp2((m_used - mx) * p.scale_log2);
 #pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[16];
+            tmem_ld16(t_lane + 128 + q * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(t_lane + 128 + q * 16, o);
+          }
+          tmem_st_wait();
+          l *= alpha;
+          m_used = mx;
+        }
+      }
+      const float nmxs = -m_used * p.scale_log2;
+      const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
+      uint64_t lsum2 = 0ull;
+      // p = exp2(s*scale - m*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
+      auto exp_block = [&](auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+#pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_lane + c * 32, v);
-          tmem_ld_wait();
-          float e[32];
+          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
-            const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scale2, nmxs2);
+            const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), scale2, nmxs2);
             float a0, a1;
             unpack_f2(t, a0, a1);
             a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower, twice: the extra
@@ -158,63 +211,49 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
               if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
               if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
             }
-            e[i] = a0; e[i + 1] = a1;
             lsum2 = add_f2(lsum2, pack_f2(a0, a1));
+            pk[i >> 1] = pack_bf16(a0, a1);
           }
           uint8_t* half_base = prow + (c >> 1) * kTile;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const int chunk = (c & 1) * 4 + g;
-            uint4 u;
-            u.x = pack_bf16(e[g * 8 + 0], e[g * 8 + 1]); u.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
-            u.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]); u.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
-            *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = u;
+            *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
           }
         }
       };
-      if (full) softmax_block(std::true_type{}); else softmax_block(std::false_type{});
+      if (full) exp_block(std::true_type{}); else exp_block(std::false_type{});
       float ls0, ls1;
       unpack_f2(lsum2, ls0, ls1);
-      l = l * alpha + (ls0 + ls1);
-      m = mx;
+      l += ls0 + ls1;
       fence_proxy_async();            // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
-      // rescale the running output while the PV MMA runs; skipped when no row of the warp raised its max
-      if (__any_sync(0xffffffffu, alpha != 1.f)) {
-        const uint64_t al2 = pack_f2(alpha, alpha);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o2[i] = mul_f2(o2[i], al2);
-      }
-      mbar_wait(&bars->o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_lane + 128 + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; i += 2)
-          o2[c * 16 + (i >> 1)] = add_f2(o2[c * 16 + (i >> 1)], pack_f2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
-      }
-      tc_fence_before();
     }
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) unpack_f2(o2[i], o[2 * i], o[2 * i + 1]);
+    mbar_wait(&bars->o_done, (nkv - 1) & 1);
+    tc_fence_after();
     const int qi = qblk * kQ + r;
-    if (qi < p.lq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* dst = p.out + ((long long)b * p.lq + qi) * p.ldo + head * kD;
+    const float inv = 1.f / l;
+    __nv_bfloat16* dst = p.out + ((long long)b * p.lq + qi) * p.ldo + head * kD;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 u;
-        u.x = pack_bf16(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv); u.y = pack_bf16(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-        u.z = pack_bf16(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv); u.w = pack_bf16(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = u;
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld32(t_lane + 128 + c * 32, o);
+      tmem_ld_wait();
+      if (qi < p.lq) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = u;
+        }
       }
     }
+    tc_fence_before();
   }
   tc_fence_before();
   __syncthreads();
