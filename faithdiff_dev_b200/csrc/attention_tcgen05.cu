@@ -19,10 +19,12 @@ extern int64_t g_launches;
 
 struct AttnParams {
   CUtensorMap qmap, kmap, vmap;
+  CUtensorMap omap;    // short-KV kernel: output as (cols, lq, batch) so a 32-row box is clipped at the end of each batch
   __nv_bfloat16* out;
   long long ldo;
   int lq, lk, heads;
   float scale_log2;
+  int q_per_cta;       // short-KV kernel: consecutive 128-query blocks of one (batch, head) handled by one CTA
 };
 
 constexpr int kQ = 128, kKV = 128, kD = 64;
@@ -262,6 +264,224 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     tmem_dealloc(tmem, 256);
   }
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Keys fit one block (lk <= 128: the UNet's cross-attention over 77 text tokens).  There is no key loop to hide latencies
+// in, so one CTA keeps K and V resident and streams `q_per_cta` query blocks of its (batch, head) through a pipeline:
+// Q double-buffered in smem, S_{i+1} = Q_{i+1} K^T issued while block i is in its exponentials, O double-buffered in TMEM
+// (cols [128,192) / [192,256)) so the normalise-and-store of block i-1 runs after P_i has been handed to the tensor core.
+struct __align__(8) AttnShortBars {
+  uint64_t kv_full, q_full[2], q_empty[2], s_full, s_read, p_full, o_done[2], o_read[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kTile;
+  uint8_t* sQ = smem + 2 * kTile;        // 2 stages
+  uint8_t* sP = smem + 4 * kTile;        // 2 halves (64 keys each)
+  uint8_t* sO = smem + 6 * kTile;        // output staging: 4 warps x (32 rows x 128 B), 128B-swizzled, TMA-stored
+  AttnShortBars* bars = reinterpret_cast<AttnShortBars*>(smem + 7 * kTile);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int nqb = (p.lq + kQ - 1) / kQ;
+  const int first = blockIdx.x * p.q_per_cta;
+  const int n_it = min(p.q_per_cta, nqb - first);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap); tma_prefetch_desc(&p.omap);
+    mbar_init(&bars->kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars->q_full[s], 1); mbar_init(&bars->q_empty[s], 1);
+      mbar_init(&bars->o_done[s], 1); mbar_init(&bars->o_read[s], 4);
+    }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_read, 4);
+    mbar_init(&bars->p_full, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&bars->tmem_base, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&bars->kv_full, 2 * kTile);
+      tma_load_2d(&p.kmap, &bars->kv_full, sK, head * kD, b * p.lk);
+      tma_load_2d(&p.vmap, &bars->kv_full, sV, head * kD, b * p.lk);
+      for (int i = 0; i < n_it; ++i) {
+        const int s = i & 1;
+        mbar_wait(&bars->q_empty[s], ((i >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&bars->q_full[s], kTile);
+        tma_load_2d(&p.qmap, &bars->q_full[s], sQ + s * kTile, head * kD, b * p.lq + (first + i) * kQ);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(128, ((p.lk + 31) >> 5) * 32, 1, 0, 0);   // only the 32-key chunks that hold keys
+      const uint32_t idesc_o = umma_idesc(128, 64, 1, 0, 1);   // B (=V) is MN-major
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+      const int nk16 = (p.lk + 15) >> 4;                         // P V over the 16-key steps that hold keys
+      auto issue_s = [&](int i) {
+        mbar_wait(&bars->q_full[i & 1], (i >> 1) & 1);
+        if (i > 0) mbar_wait(&bars->s_read, (i - 1) & 1);    // every softmax warp holds S_{i-1} in registers
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + (i & 1) * kTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
+        tc_commit(&bars->s_full);
+        tc_commit(&bars->q_empty[i & 1]);
+      };
+      mbar_wait(&bars->kv_full, 0);
+      issue_s(0);
+      for (int i = 0; i < n_it; ++i) {
+        if (i + 1 < n_it) issue_s(i + 1);
+        mbar_wait(&bars->p_full, i & 1);
+        if (i >= 2) mbar_wait(&bars->o_read[i & 1], ((i - 2) >> 1) & 1);   // O_{i-2} has been copied out of this buffer
+        tc_fence_after();
+        for (int k = 0; k < nk16; ++k)
+          umma_f16(tmem + 128 + (i & 1) * 64, umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                   umma_desc_sw128(aV + k * 2048, 0, 1024), idesc_o, k != 0);
+        tc_commit(&bars->o_done[i & 1]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                       // query row within the block
+    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
+    uint8_t* prow = sP + r * 128;
+    const int sw = r & 7;
+    const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
+    const int nfull = p.lk >> 5;                          // 32-key chunks entirely inside the key range
+    const bool partial = (p.lk & 31) != 0;                // ... followed by one straddling chunk
+    uint8_t* stage = sO + quad * 4096 + lane * 128;       // this thread's 128-byte output row in the warp's staging box
+    // normalise O_i (TMEM buffer i&1) by the row sum and hand the warp's 32 x 64 box to TMA (a row-per-thread store to global
+    // memory is 32 different lines per instruction; it cost as much as the exponentials)
+    auto store_block = [&](int i, float l) {
+      const float inv = 1.f / l;
+      if (lane == 0) bulk_wait_read<0>();                 // the previous box has left the staging buffer
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld32(t_lane + 128 + (i & 1) * 64 + c * 32, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 u;
+          u.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
+          u.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
+          u.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
+          u.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(stage + (((c * 4 + g) ^ sw) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars->o_read[i & 1]);
+        tma_store_3d(&p.omap, sO + quad * 4096, head * kD, (first + i) * kQ + quad * 32, b);
+        bulk_commit();
+      }
+    };
+    float l_prev = 1.f;
+    for (int i = 0; i < n_it; ++i) {
+      mbar_wait(&bars->s_full, i & 1);
+      tc_fence_after();
+      uint32_t v[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c * 32 < p.lk) tmem_ld32(t_lane + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->s_read);          // the tensor core may now compute S_{i+1}
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nfull) {
+          float m1 = mx, m2 = mx, m3 = mx;
+#pragma unroll
+          for (int k = c * 32; k < c * 32 + 32; k += 8) {
+            mx = max3_f(mx, __uint_as_float(v[k]), __uint_as_float(v[k + 1]));
+            m1 = max3_f(m1, __uint_as_float(v[k + 2]), __uint_as_float(v[k + 3]));
+            m2 = max3_f(m2, __uint_as_float(v[k + 4]), __uint_as_float(v[k + 5]));
+            m3 = max3_f(m3, __uint_as_float(v[k + 6]), __uint_as_float(v[k + 7]));
+          }
+          mx = fmaxf(max3_f(mx, m1, m2), m3);
+        } else if (c == nfull && partial) {
+#pragma unroll
+          for (int k = c * 32; k < c * 32 + 32; ++k)
+            if (k < p.lk) mx = fmaxf(mx, __uint_as_float(v[k]));
+        }
+      }
+      if (i > 0) {
+        mbar_wait(&bars->o_done[(i - 1) & 1], ((i - 1) >> 1) & 1);   // P_{i-1} V finished: sP may be rewritten, O_{i-1} is final
+        tc_fence_after();
+      }
+      const float nmxs = -mx * p.scale_log2;
+      const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
+      uint64_t lsum2 = 0ull;
+      auto exp_chunk = [&](int c, auto full_tag) {
+        constexpr bool kFull = decltype(full_tag)::value;
+        uint32_t pk[16];
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + k]), __uint_as_float(v[c * 32 + k + 1])), scale2, nmxs2);
+          float a0, a1;
+          unpack_f2(t, a0, a1);
+          a0 = fast_exp2(a0);
+          a1 = fast_exp2(a1);
+          if constexpr (!kFull) {
+            if (c * 32 + k >= p.lk) a0 = 0.f;
+            if (c * 32 + k + 1 >= p.lk) a1 = 0.f;
+          }
+          lsum2 = add_f2(lsum2, pack_f2(a0, a1));
+          pk[k >> 1] = pack_bf16(a0, a1);
+        }
+        uint8_t* half_base = prow + (c >> 1) * kTile;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        }
+      };
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < nfull) exp_chunk(c, std::true_type{});
+        else if (c == nfull && partial) exp_chunk(c, std::false_type{});
+      }
+      float ls0, ls1;
+      unpack_f2(lsum2, ls0, ls1);
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->p_full);
+      if (i > 0) store_block(i - 1, l_prev);              // while the tensor core computes P_i V
+      l_prev = ls0 + ls1;
+    }
+    mbar_wait(&bars->o_done[(n_it - 1) & 1], ((n_it - 1) >> 1) & 1);
+    tc_fence_after();
+    store_block(n_it - 1, l_prev);
+    if (lane == 0) bulk_wait<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
 }  // namespace fd
 
 using namespace fd;
@@ -288,13 +508,33 @@ extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.lq = lq; p.lk = lk; p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
   const size_t smem_bytes = 7 * kTile + sizeof(AttnBars);
+  const size_t smem_short = 7 * kTile + sizeof(AttnShortBars);
   static bool attr = false;
   if (!attr) {
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_shortkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_short));
     attr = true;
   }
-  dim3 grid((lq + kQ - 1) / kQ, heads, batch);
-  FD_CHECK_CUDA(launch_pdl(attention_d64_kernel, grid, dim3(192), smem_bytes, stream, 1, p));
+  const int nqb = (lq + kQ - 1) / kQ;
+  if (lk <= kKV) {
+    // as few query blocks per CTA as still fit all CTAs in one wave (two CTAs per SM)
+    const long long slots = 2ll * num_sms();
+    int qpc = 1;
+    while (qpc < nqb && (long long)((nqb + qpc - 1) / qpc) * heads * batch > slots) ++qpc;
+    { const char* e = getenv("FD_ATTN_QPC"); if (e && atoi(e) > 0) qpc = atoi(e) < nqb ? atoi(e) : nqb; }   // tuning override
+    p.q_per_cta = qpc;
+    {
+      uint64_t dims[3] = {(uint64_t)heads * kD, (uint64_t)lq, (uint64_t)batch};
+      uint64_t str[2] = {(uint64_t)ldo * 2, (uint64_t)ldo * 2 * lq};
+      uint32_t box[3] = {kD, 32, 1};
+      if (encode_tensor_map(&p.omap, out, 3, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
+    }
+    dim3 grid((nqb + qpc - 1) / qpc, heads, batch);
+    FD_CHECK_CUDA(launch_pdl(attention_d64_shortkv_kernel, grid, dim3(192), smem_short, stream, 1, p));
+  } else {
+    dim3 grid(nqb, heads, batch);
+    FD_CHECK_CUDA(launch_pdl(attention_d64_kernel, grid, dim3(192), smem_bytes, stream, 1, p));
+  }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

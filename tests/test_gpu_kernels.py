@@ -79,7 +79,8 @@ def test_conv3x3(ops, B, H, W, C0, C1, N, stride, pad_lo):
     assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
 
 
-@pytest.mark.parametrize("B,heads,lq,lk", [(2, 2, 256, 256), (2, 10, 4096, 4096), (2, 4, 1024, 77), (1, 1, 16, 16), (2, 3, 200, 333)])
+@pytest.mark.parametrize("B,heads,lq,lk", [(2, 2, 256, 256), (2, 10, 4096, 4096), (2, 4, 1024, 77), (1, 1, 16, 16), (2, 3, 200, 333),
+                                           (3, 20, 1000, 77), (1, 2, 2048, 128)])
 def test_attention_d64(ops, B, heads, lq, lk):
     torch.manual_seed(3)
     C = heads * 64
@@ -89,6 +90,25 @@ def test_attention_d64(ops, B, heads, lq, lk):
     qq = q.float().view(B, lq, heads, 64).transpose(1, 2)
     kk = kv[:, :C].float().reshape(B, lk, heads, 64).transpose(1, 2)
     vv = kv[:, C:].float().reshape(B, lk, heads, 64).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * lq, C)
+    assert rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("lq,lk", [(256, 1024), (300, 77), (128, 700)])
+def test_attention_d64_growing_max(ops, lq, lk):
+    """Logits whose row maximum keeps growing along the key axis (by far more than 2^8 per block): exercises the in-place
+    rescale of the TMEM-resident output accumulator, and rows whose maximum sits in a partially masked last block."""
+    torch.manual_seed(31)
+    B, heads = 2, 3
+    C = heads * 64
+    q = (torch.randn(B * lq, C, device="cuda") * 3).to(BF)
+    ramp = torch.linspace(0.2, 4.0, lk, device="cuda").repeat(B)[:, None]
+    k = (torch.randn(B * lk, C, device="cuda") * ramp).to(BF)
+    v = torch.randn(B * lk, C, device="cuda").to(BF)
+    out = ops.attention(q, k, v, B, heads, lq, lk, 0.125)
+    qq = q.float().view(B, lq, heads, 64).transpose(1, 2)
+    kk = k.float().view(B, lk, heads, 64).transpose(1, 2)
+    vv = v.float().view(B, lk, heads, 64).transpose(1, 2)
     ref = F.scaled_dot_product_attention(qq, kk, vv).transpose(1, 2).reshape(B * lq, C)
     assert rel(out, ref) < 1e-2
 
