@@ -7,6 +7,7 @@ from .scheduler import DDPMScheduler, EulerDiscreteScheduler  # noqa: F401
 from .tiling import LocalAttention  # noqa: F401
 from .unet import UNet2DConditionModel  # noqa: F401
 from .vae import AutoencoderKL, Encoder  # noqa: F401
+from .text_encoder import CLIPTextEncoder, CLIP_L_CONFIG, OPENCLIP_BIGG_CONFIG  # noqa: F401
 from .color_fix import adain_color_fix, wavelet_color_fix  # noqa: F401
 from .create_model import FaithDiff_pipeline, quantize_8bit_state_dict  # noqa: F401
 from .image_process import check_image_size  # noqa: F401

@@ -40,6 +40,7 @@ i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 _SIGS = {
     "fd_gemm": [C.POINTER(GemmDesc), vp],
     "fd_attention_d64": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
+    "fd_attention_d64_causal": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
     "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
     "fd_groupnorm_work_floats": [i32, i32, i32],
     "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],

@@ -10,6 +10,7 @@ import torch
 from . import arch
 from .pipeline import FaithDiffStableDiffusionXLPipeline
 from .scheduler import DDPMScheduler, EulerDiscreteScheduler
+from .text_encoder import CLIPTextEncoder
 from .unet import UNet2DConditionModel
 from .vae import AutoencoderKL
 
@@ -27,6 +28,34 @@ def _find(dirpath, patterns):
         if hits:
             return hits[0]
     raise FileNotFoundError("none of %s under %s" % (patterns, dirpath))
+
+
+def load_text_encoder(dirpath):
+    """`<sdxl>/text_encoder{,_2}` (transformers layout: config.json + model*.safetensors) → CLIPTextEncoder on B200 kernels;
+    None when the directory is absent (the pipeline then needs prompt_embeds)."""
+    import json
+    cfg_file = os.path.join(dirpath, "config.json")
+    if not os.path.isfile(cfg_file):
+        return None
+    cfg = json.load(open(cfg_file))
+    with_proj = "WithProjection" in "".join(cfg.get("architectures") or [])
+    enc = CLIPTextEncoder(vocab_size=cfg["vocab_size"], hidden_size=cfg["hidden_size"], intermediate_size=cfg["intermediate_size"],
+                          num_hidden_layers=cfg["num_hidden_layers"], num_attention_heads=cfg["num_attention_heads"],
+                          max_position_embeddings=cfg.get("max_position_embeddings", 77), hidden_act=cfg.get("hidden_act", "quick_gelu"),
+                          layer_norm_eps=cfg.get("layer_norm_eps", 1e-5), eos_token_id=cfg.get("eos_token_id", 2),
+                          projection_dim=cfg.get("projection_dim") if with_proj else None)
+    return enc.load_state_dict(_load_file(_find(dirpath, ["model.fp16.safetensors", "model*.safetensors", "*.bin"])), strict=False)
+
+
+def load_tokenizer(dirpath):
+    """CLIP BPE tokenizer files are plain text/json; the tokenizer itself is host-side string processing (transformers)."""
+    if not os.path.isdir(dirpath):
+        return None
+    try:
+        from transformers import CLIPTokenizer
+        return CLIPTokenizer.from_pretrained(dirpath)
+    except Exception:
+        return None
 
 
 def quantize_8bit_state_dict(sd):
@@ -51,7 +80,10 @@ def FaithDiff_pipeline(sdxl_path, VAE_FP16_path, FaithDiff_path, use_fp8=False, 
     if use_fp8:
         sd = quantize_8bit_state_dict(sd)
     unet.load_state_dict(sd, strict=True)
-    pipe = FaithDiffStableDiffusionXLPipeline(vae=vae, denoise_encoder=unet.denoise_encoder, text_encoder=None, text_encoder_2=None,
-                                              tokenizer=None, tokenizer_2=None, unet=unet, scheduler=EulerDiscreteScheduler(),
-                                              DDPM_scheduler=DDPMScheduler())
+    pipe = FaithDiffStableDiffusionXLPipeline(vae=vae, denoise_encoder=unet.denoise_encoder,
+                                              text_encoder=load_text_encoder(os.path.join(sdxl_path, "text_encoder")),
+                                              text_encoder_2=load_text_encoder(os.path.join(sdxl_path, "text_encoder_2")),
+                                              tokenizer=load_tokenizer(os.path.join(sdxl_path, "tokenizer")),
+                                              tokenizer_2=load_tokenizer(os.path.join(sdxl_path, "tokenizer_2")), unet=unet,
+                                              scheduler=EulerDiscreteScheduler(), DDPM_scheduler=DDPMScheduler())
     return pipe

@@ -24,6 +24,7 @@ struct AttnParams {
   long long ldo;
   int lq, lk, heads;
   float scale_log2;
+  int causal;          // short-KV kernel only: key k attends to query q iff k <= q (CLIP text encoders)
   int q_per_cta;       // short-KV kernel: consecutive 128-query blocks of one (batch, head) handled by one CTA
 };
 
@@ -361,8 +362,8 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
     uint8_t* prow = sP + r * 128;
     const int sw = r & 7;
     const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
-    const int nfull = p.lk >> 5;                          // 32-key chunks entirely inside the key range
-    const bool partial = (p.lk & 31) != 0;                // ... followed by one straddling chunk
+    const int nfull = p.causal ? 0 : (p.lk >> 5);         // 32-key chunks no row needs a mask for
+    const int nch = (p.lk + 31) >> 5;                     // chunks holding keys at all (the rest of S is never read)
     uint8_t* stage = sO + quad * 4096 + lane * 128;       // this thread's 128-byte output row in the warp's staging box
     // normalise O_i (TMEM buffer i&1) by the row sum and hand the warp's 32 x 64 box to TMA (a row-per-thread store to global
     // memory is 32 different lines per instruction; it cost as much as the exponentials)
@@ -406,6 +407,8 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_read);          // the tensor core may now compute S_{i+1}
+      // keys this row may attend to: [0, limit)
+      const int limit = p.causal ? min(p.lk, (first + i) * kQ + r + 1) : p.lk;
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -419,10 +422,10 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
             m3 = max3_f(m3, __uint_as_float(v[k + 6]), __uint_as_float(v[k + 7]));
           }
           mx = fmaxf(max3_f(mx, m1, m2), m3);
-        } else if (c == nfull && partial) {
+        } else if (c < nch) {
 #pragma unroll
           for (int k = c * 32; k < c * 32 + 32; ++k)
-            if (k < p.lk) mx = fmaxf(mx, __uint_as_float(v[k]));
+            if (k < limit) mx = fmaxf(mx, __uint_as_float(v[k]));
         }
       }
       if (i > 0) {
@@ -443,8 +446,8 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
           a0 = fast_exp2(a0);
           a1 = fast_exp2(a1);
           if constexpr (!kFull) {
-            if (c * 32 + k >= p.lk) a0 = 0.f;
-            if (c * 32 + k + 1 >= p.lk) a1 = 0.f;
+            if (c * 32 + k >= limit) a0 = 0.f;
+            if (c * 32 + k + 1 >= limit) a1 = 0.f;
           }
           lsum2 = add_f2(lsum2, pack_f2(a0, a1));
           pk[k >> 1] = pack_bf16(a0, a1);
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < nfull) exp_chunk(c, std::true_type{});
-        else if (c == nfull && partial) exp_chunk(c, std::false_type{});
+        else if (c < nch) exp_chunk(c, std::false_type{});
       }
       float ls0, ls1;
       unpack_f2(lsum2, ls0, ls1);
@@ -486,9 +489,11 @@ __global__ void __launch_bounds__(192, 2) attention_d64_shortkv_kernel(const __g
 
 using namespace fd;
 
-extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
-                                int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream_) {
+static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                              int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, int causal,
+                              void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  FD_REQUIRE(!causal || lk <= kKV, "fd_attention_d64_causal: at most %d keys (got %d)", kKV, lk);
   FD_REQUIRE(q && k && v && out && batch > 0 && heads > 0 && lq > 0 && lk > 0, "fd_attention_d64: bad arguments");
   FD_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "fd_attention_d64: pitches must be multiples of 8");
   FD_REQUIRE(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0,
@@ -507,6 +512,7 @@ extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64
   }
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.lq = lq; p.lk = lk; p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
+  p.causal = causal;
   const size_t smem_bytes = 7 * kTile + sizeof(AttnBars);
   const size_t smem_short = 7 * kTile + sizeof(AttnShortBars);
   static bool attr = false;
@@ -538,4 +544,15 @@ extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                                int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream) {
+  return attention_d64_impl(q, ldq, k, ldk, v, ldv, out, ldo, batch, heads, lq, lk, scale, 0, stream);
+}
+
+extern "C" int fd_attention_d64_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                       void* out, int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale,
+                                       void* stream) {
+  return attention_d64_impl(q, ldq, k, ldk, v, ldv, out, ldo, batch, heads, lq, lk, scale, 1, stream);
 }

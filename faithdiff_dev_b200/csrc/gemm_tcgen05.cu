@@ -358,6 +358,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         } else if (act == 3) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = quick_gelu_f(x[j]);
+        } else if (act == 4) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = gelu_erf_f(x[j]);
         }
       };
       // GEGLU: the chunk's columns are interleaved (h, g) pairs -> 16 outputs h * gelu(g)

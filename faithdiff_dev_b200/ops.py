@@ -89,11 +89,12 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
     return out
 
 
-def attention(q, k, v, batch, heads, lq, lk, scale, out=None):
+def attention(q, k, v, batch, heads, lq, lk, scale, out=None, causal=False):
     """q [batch*lq, >=heads*64] / k, v [batch*lk, ...] bf16 row views (unit inner stride) -> out [batch*lq, heads*64]."""
     if out is None:
         out = torch.empty((batch * lq, heads * 64), device=q.device, dtype=BF16)
-    check(lib.fd_attention_d64(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), batch,
+    fn = lib.fd_attention_d64_causal if causal else lib.fd_attention_d64
+    check(fn(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), batch,
                                heads, lq, lk, scale, _stream()), "fd_attention_d64")
     return out
 

@@ -163,12 +163,81 @@ class FaithDiffStableDiffusionXLPipeline:
         if negative_prompt_embeds is not None and negative_pooled_prompt_embeds is None:
             raise ValueError("If `negative_prompt_embeds` are provided, `negative_pooled_prompt_embeds` also have to be passed.")
 
-    def encode_prompt(self, prompt, negative_prompt=None, **kw):
-        """Prompt encoding (pipeline…:485-717) is the caller immediately before the hot path (SURVEY §8f rank 1,
-        'next'): it needs the CLIP text encoders + tokenizers, which are torch/transformers modules outside this
-        round's scope.  Pass prompt_embeds / pooled_prompt_embeds (the reference accepts but ignores them)."""
-        raise NotImplementedError("encode_prompt: pass prompt_embeds/negative_prompt_embeds/pooled_prompt_embeds/"
-                                  "negative_pooled_prompt_embeds; the CLIP text encoders are not part of the B200 hot path yet")
+    def encode_prompt(self, prompt=None, prompt_2=None, device=None, num_images_per_prompt=1, do_classifier_free_guidance=True,
+                      negative_prompt=None, negative_prompt_2=None, prompt_embeds=None, negative_prompt_embeds=None,
+                      pooled_prompt_embeds=None, negative_pooled_prompt_embeds=None, lora_scale=None, clip_skip=None,
+                      input_ids=None, input_ids_2=None, negative_input_ids=None, negative_input_ids_2=None):
+        """SDXL prompt encoding, pipeline…:485-717: both text encoders over the (padded, truncated) 77 token ids,
+        `hidden_states[-2]` (or `-(clip_skip+2)`) of each concatenated along channels, pooled output of the LAST encoder;
+        negative branch = zeros when no negative prompt is given and `force_zeros_for_empty_prompt` (SDXL default), else
+        the encoded negative prompt ("" by default).  Superset of the reference: pre-computed `prompt_embeds` are honoured
+        (the reference ignores them, :1237-1243) and token ids can be passed directly (`input_ids*`) so no tokenizer is
+        needed.  The encoders are `faithdiff_dev_b200.CLIPTextEncoder` (B200 kernels) or anything with the same call."""
+        if lora_scale is not None:
+            raise NotImplementedError("encode_prompt: LoRA scaling of the text encoders")
+        encoders = [e for e in (self.text_encoder, self.text_encoder_2) if e is not None]
+        tokenizers = [t for t in (self.tokenizer, self.tokenizer_2)] if self.text_encoder is not None else [self.tokenizer_2]
+        if prompt_embeds is None and not encoders:
+            raise RuntimeError("encode_prompt: the pipeline was built without text encoders; pass prompt_embeds / "
+                               "pooled_prompt_embeds, or construct it with faithdiff_dev_b200.CLIPTextEncoder instances")
+
+        def ids_for(which, text, given, max_length=None):
+            if given is not None:
+                return torch.as_tensor(given).reshape(-1, torch.as_tensor(given).shape[-1]).to(torch.int64)
+            tok = tokenizers[which]
+            if tok is None:
+                raise RuntimeError("encode_prompt: no tokenizer %d; pass input_ids instead of text" % (which + 1))
+            return tok(text, padding="max_length", max_length=max_length or tok.model_max_length, truncation=True,
+                       return_tensors="pt").input_ids
+
+        def run(texts, given_ids, skip, max_length=None):
+            embeds, pooled = [], None
+            for which, enc in enumerate(encoders):
+                out = enc(ids_for(which, texts[which], given_ids[which], max_length), output_hidden_states=True)
+                pooled = out[0]                                  # only the final encoder's survives (pipeline…:608)
+                embeds.append(out.hidden_states[-2] if skip is None else out.hidden_states[-(skip + 2)])
+            return torch.cat(embeds, dim=-1), pooled
+
+        if isinstance(prompt, str):
+            prompt = [prompt]
+        if prompt is not None:
+            batch_size = len(prompt)
+        elif prompt_embeds is not None:
+            batch_size = prompt_embeds.shape[0]
+        else:
+            batch_size = torch.as_tensor(input_ids).reshape(-1, torch.as_tensor(input_ids).shape[-1]).shape[0]
+        if prompt_embeds is None:
+            p2 = prompt_2 or prompt
+            p2 = [p2] if isinstance(p2, str) else p2
+            ids2 = input_ids_2 if input_ids_2 is not None else input_ids
+            prompt_embeds, pooled_prompt_embeds = run([prompt, p2], [input_ids, ids2], clip_skip)
+        zero_neg = negative_prompt is None and negative_input_ids is None and self.config.get("force_zeros_for_empty_prompt", True)
+        if do_classifier_free_guidance and negative_prompt_embeds is None:
+            if zero_neg:
+                negative_prompt_embeds = torch.zeros_like(prompt_embeds)
+                negative_pooled_prompt_embeds = torch.zeros_like(pooled_prompt_embeds)
+            else:
+                negative_prompt = negative_prompt or ""
+                negative_prompt_2 = negative_prompt_2 or negative_prompt
+                neg = batch_size * [negative_prompt] if isinstance(negative_prompt, str) else negative_prompt
+                neg2 = batch_size * [negative_prompt_2] if isinstance(negative_prompt_2, str) else negative_prompt_2
+                if prompt is not None and negative_input_ids is None and batch_size != len(neg):
+                    raise ValueError(f"`negative_prompt`: {negative_prompt} has batch size {len(neg)}, but `prompt`: {prompt} has "
+                                     f"batch size {batch_size}.")
+                nids2 = negative_input_ids_2 if negative_input_ids_2 is not None else negative_input_ids
+                negative_prompt_embeds, negative_pooled_prompt_embeds = run([neg, neg2], [negative_input_ids, nids2], None,
+                                                                            max_length=prompt_embeds.shape[1])
+        dt = BF16
+        bs, seq, _ = prompt_embeds.shape
+        prompt_embeds = prompt_embeds.to(self.device, dt).repeat(1, num_images_per_prompt, 1).view(bs * num_images_per_prompt, seq, -1)
+        pooled_prompt_embeds = pooled_prompt_embeds.to(self.device, dt).repeat(1, num_images_per_prompt).view(bs * num_images_per_prompt, -1)
+        if do_classifier_free_guidance:
+            seq = negative_prompt_embeds.shape[1]
+            negative_prompt_embeds = negative_prompt_embeds.to(self.device, dt).repeat(1, num_images_per_prompt, 1).view(
+                batch_size * num_images_per_prompt, seq, -1)
+            negative_pooled_prompt_embeds = negative_pooled_prompt_embeds.to(self.device, dt).repeat(1, num_images_per_prompt).view(
+                bs * num_images_per_prompt, -1)
+        return prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds
 
     # ------------------------------------------------------------------ stages
     def _preprocess(self, lr_img, height, width):
@@ -222,7 +291,8 @@ class FaithDiffStableDiffusionXLPipeline:
                           pooled_prompt_embeds, negative_pooled_prompt_embeds)
         if prompt_embeds is None:
             prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
-                prompt, negative_prompt=negative_prompt)
+                prompt, prompt_2, negative_prompt=negative_prompt, negative_prompt_2=negative_prompt_2, clip_skip=clip_skip,
+                num_images_per_prompt=num_images_per_prompt)
         dev, dt = self.device, BF16
         unet, vae, sch = self.unet, self.vae, self.scheduler
         ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "enc", "loop", "dec")}

@@ -41,7 +41,8 @@ typedef struct fd_gemm_desc {
   int32_t mode;
   int32_t batch, in_h, in_w; /* conv input geometry                                                       */
   int32_t pad_lo;        /* zero padding at top/left (1: pad=1; 0: the VAE's F.pad(0,1,0,1) + pad 0)      */
-  int32_t act;           /* 0 none, 1 SiLU, 2 GEGLU (B rows interleaved h0,g0,h1,g1… → N/2 outputs), 3 QuickGELU */
+  int32_t act;           /* 0 none, 1 SiLU, 2 GEGLU (B rows interleaved h0,g0,h1,g1… → N/2 outputs), 3 QuickGELU, */
+                         /* 4 GELU (erf form; OpenCLIP-bigG text encoder MLP)                                   */
   int32_t bias_along_m;  /* bias indexed by output row instead of column                                  */
   int32_t out_fp32;      /* out dtype: 0 bf16, 1 fp32                                                     */
   const float* bias;     /* [N] (or [M]) fp32, or NULL                                                    */
@@ -67,6 +68,12 @@ int fd_sizeof_gemm_desc(void);   /* lets a foreign-language binding verify its s
  * --------------------------------------------------------------------------------------------------------- */
 int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                      int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream);
+/* Same, causal (key j is visible to query i iff j <= i), lk <= 128.
+ * Replaces: the causal self-attention of the CLIP text encoders (transformers CLIPAttention with the causal mask built in
+ * CLIPTextTransformer.forward) that pipeline_FaithDiff_tlc.py:605 (`text_encoder(text_input_ids, output_hidden_states=True)`)
+ * runs for encode_prompt — SURVEY §8f rank 1.                                                                          */
+int fd_attention_d64_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
+                            int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream);
 
 /* row softmax: p[r, :] = softmax(alpha * s[r, :]) ; s fp32 [rows, ld_s], p bf16 [rows, ld_p]
  * (single-head d=512 attention of the VAE / LQ-encoder mid block, unet_…extension.py:96-106)              */

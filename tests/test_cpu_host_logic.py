@@ -165,3 +165,25 @@ def test_quantize_8bit_state_dict():
     assert torch.equal(q["denoise_encoder.conv_in.weight"], sd["denoise_encoder.conv_in.weight"])
     ref = sd["conv_in.weight"].to(torch.float8_e4m3fn).float()
     assert torch.equal(q["conv_in.weight"], ref) and not torch.equal(ref, sd["conv_in.weight"])
+
+
+def test_text_encoder_host_logic():
+    """encode_prompt host pieces that need no GPU: pooled-token row (transformers CLIPTextTransformer semantics) and the
+    ModelOutput-style indexing the reference relies on (`prompt_embeds[0]`, `.hidden_states[-2]`, pipeline…:605-612)."""
+    import torch
+    from faithdiff_dev_b200.text_encoder import CLIP_L_CONFIG, OPENCLIP_BIGG_CONFIG, CLIPTextEncoder, TextEncoderOutput, eos_positions
+    ids = torch.tensor([[49406, 320, 1125, 49407, 49407, 49407], [49406, 5, 6, 7, 8, 49407]])
+    assert eos_positions(ids, 2).tolist() == [3, 5]                 # legacy config: argmax (first max)
+    assert eos_positions(ids, 49407).tolist() == [3, 5]             # first occurrence of the eos id
+    assert eos_positions(torch.tensor([[1, 9, 4, 9]]), 9).tolist() == [1]
+    last, pooled, hs, te = object(), object(), (1, 2, 3), object()
+    assert TextEncoderOutput(last, pooled, hs, None)[0] is last and TextEncoderOutput(last, pooled, hs, None)[1] is pooled
+    assert TextEncoderOutput(last, pooled, hs, te)[0] is te and TextEncoderOutput(last, pooled, hs, te)[1] is last
+    assert TextEncoderOutput(last, pooled, hs, te)[2] is hs
+    assert CLIP_L_CONFIG["hidden_size"] == 64 * CLIP_L_CONFIG["num_attention_heads"]
+    assert OPENCLIP_BIGG_CONFIG["hidden_size"] == 64 * OPENCLIP_BIGG_CONFIG["num_attention_heads"]
+    import pytest
+    with pytest.raises(ValueError):
+        CLIPTextEncoder(hidden_size=640, num_attention_heads=8)     # 80-wide heads: not this kernel
+    with pytest.raises(RuntimeError):
+        CLIPTextEncoder()(ids)                                      # weights not loaded
