@@ -19,7 +19,7 @@ def agg(lo,hi,title):
         print("   %-32s x%5d %10.1f us %5.1f%%"%(n[:32],c,t,100*t/S))
 i0=names.index('scale_div_kernel') if 'scale_div_kernel' in names else 0
 i1=names.index('tile_blend_kernel', i0)+1 if 'tile_blend_kernel' in names[i0:] else len(seq)
-agg(0,i0,'encode (LQ encoder + VAE encode + cond)'); agg(i0,i1,'denoise (1 step)'); agg(i1,len(seq),'decode')
+agg(0,i0,'before the first scheduler step (LQ encoder, VAE encode, condition embedding, eager warm-up of the tile-step before graph capture)'); agg(i0,i1,'one denoise step (1 tile: one UNet tile-step + fused CFG/Euler/blend tail)'); agg(i1,len(seq),'rest of the capture window (further denoise steps up to the ncu -c cap)')
 # gemm by grid size buckets in denoise
 g=[(v,gs) for n,v,gs in seq[i0:i1] if n=='gemm_tcgen05_kernel']
 print("gemm launches in denoise:",len(g),"mean us %.1f"%(sum(v for v,_ in g)/max(1,len(g))))
