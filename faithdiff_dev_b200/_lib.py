@@ -34,6 +34,7 @@ lib = _load()
 lib.fd_last_error.restype = C.c_char_p
 lib.fd_launch_count.restype = C.c_int64
 lib.fd_groupnorm_work_floats.restype = C.c_int64
+lib.fd_groupnorm_sync_bytes.restype = C.c_int64
 lib.fd_colorfix_work_floats.restype = C.c_int64
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -44,6 +45,8 @@ _SIGS = {
     "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
     "fd_groupnorm_work_floats": [i32, i32, i32],
     "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
+    "fd_groupnorm_sync_bytes": [],
+    "fd_groupnorm_nhwc_fused": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp, vp],
     "fd_layernorm": [vp, vp, vp, vp, i64, i32, f32, vp],
     "fd_upsample_nearest_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "fd_nchw_to_nhwc": [vp, i32, vp, i32, i32, i64, vp],
@@ -63,6 +66,8 @@ _SIGS = {
     "fd_seam_blend": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "fd_image_preprocess": [vp, vp, vp, i32, i32, vp],
     "fd_image_postprocess": [vp, i32, vp, i32, i32, vp],
+    "fd_resample_u8_horizontal": [vp, i32, i64, vp, i32, i32, vp, vp, i32, vp],
+    "fd_resample_u8_vertical": [vp, i64, vp, i32, vp, vp, i32, vp],
     "fd_colorfix_work_floats": [i32, i32],
     "fd_adain_color_fix": [vp, vp, vp, i32, i32, vp, vp],
     "fd_wavelet_color_fix": [vp, vp, vp, i32, i32, vp, vp],

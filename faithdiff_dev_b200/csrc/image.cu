@@ -134,6 +134,77 @@ __global__ void wavelet_final_kernel(const float* __restrict__ high, const float
     out[i] = (uint8_t)(__fmul_rn(r, 255.f));
   }
 }
+// ------------------------------------------------------------------ Pillow-compatible resample (LANCZOS upscale of the caller)
+// PIL's ImagingResample for 8-bit images (what `image.resize((w, h), Image.LANCZOS)` at test_wo_llava.py:81 runs): a horizontal
+// then a vertical pass, taps normalised and rounded to 22-bit fixed point on the host (image_process.resample_taps), int32
+// accumulation started at 1 << 21, arithmetic shift, clamp to u8, and a u8 intermediate image between the passes.  Integer work:
+// the result is bit-identical to PIL.  bounds[2*i] = first source index, bounds[2*i+1] = tap count of output index i.
+constexpr int kResampleBits = 32 - 8 - 2;
+__device__ __forceinline__ uint8_t resample_clip8(int v) {
+  v >>= kResampleBits;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+template <int CH>
+__global__ void resample_h_kernel(const uint8_t* __restrict__ in, int in_w, long long rows, uint8_t* __restrict__ out, int out_w,
+                                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const long long total = rows * out_w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int xx = (int)(i % out_w);
+    const long long y = i / out_w;
+    const int xmin = __ldg(bounds + 2 * xx), n = __ldg(bounds + 2 * xx + 1);
+    const int* k = kk + (long long)xx * ksize;
+    const uint8_t* src = in + (y * in_w + xmin) * CH;
+    int acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 1 << (kResampleBits - 1);
+    for (int x = 0; x < n; ++x) {
+      const int w = __ldg(k + x);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) acc[c] += (int)src[x * CH + c] * w;
+    }
+    uint8_t* dst = out + i * CH;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) dst[c] = resample_clip8(acc[c]);
+  }
+}
+
+// the vertical pass does not see channels: every byte column of a row is filtered alike; VEC bytes per thread
+template <int VEC>
+__global__ void resample_v_kernel(const uint8_t* __restrict__ in, long long row_bytes, uint8_t* __restrict__ out, int out_h,
+                                  const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const long long per_row = row_bytes / VEC;
+  const long long total = per_row * out_h;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int yy = (int)(i / per_row);
+    const long long col = (i - (long long)yy * per_row) * VEC;
+    const int ymin = __ldg(bounds + 2 * yy), n = __ldg(bounds + 2 * yy + 1);
+    const int* k = kk + (long long)yy * ksize;
+    int acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) acc[c] = 1 << (kResampleBits - 1);
+    for (int y = 0; y < n; ++y) {
+      const int w = __ldg(k + y);
+      const uint8_t* src = in + (long long)(ymin + y) * row_bytes + col;
+      if (VEC == 4) {
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(src));
+        acc[0] += (int)(u & 0xffu) * w; acc[1 % VEC] += (int)((u >> 8) & 0xffu) * w;
+        acc[2 % VEC] += (int)((u >> 16) & 0xffu) * w; acc[3 % VEC] += (int)(u >> 24) * w;
+      } else {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) acc[c] += (int)src[c] * w;
+      }
+    }
+    uint8_t* dst = out + (long long)yy * row_bytes + col;
+    if (VEC == 4) {
+      *reinterpret_cast<uint32_t*>(dst) = (uint32_t)resample_clip8(acc[0]) | ((uint32_t)resample_clip8(acc[1 % VEC]) << 8) |
+                                          ((uint32_t)resample_clip8(acc[2 % VEC]) << 16) | ((uint32_t)resample_clip8(acc[3 % VEC]) << 24);
+    } else {
+#pragma unroll
+      for (int c = 0; c < VEC; ++c) dst[c] = resample_clip8(acc[c]);
+    }
+  }
+}
 }  // namespace fd
 
 using namespace fd;
@@ -194,6 +265,35 @@ extern "C" int fd_wavelet_color_fix(const uint8_t* target, const uint8_t* source
   }
   wavelet_final_kernel<<<ew_grid(hw * 3), 256, 0, stream>>>(high, a + 3 * hw, out, hw);
   g_launches += 7;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_resample_u8_horizontal(const uint8_t* in, int32_t in_w, int64_t rows, uint8_t* out, int32_t out_w, int32_t channels,
+                                         const int32_t* bounds, const int32_t* taps, int32_t ksize, void* stream_) {
+  FD_REQUIRE(in && out && bounds && taps, "fd_resample_u8_horizontal: null pointer");
+  FD_REQUIRE(channels >= 1 && channels <= 4 && in_w > 0 && out_w > 0 && rows >= 0 && ksize > 0, "fd_resample_u8_horizontal: bad shape");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const unsigned grid = ew_grid(rows * out_w);
+#define FD_RH(C) resample_h_kernel<C><<<grid, 256, 0, st>>>(in, in_w, (long long)rows, out, out_w, bounds, taps, ksize)
+  if (channels == 1) FD_RH(1); else if (channels == 2) FD_RH(2); else if (channels == 3) FD_RH(3); else FD_RH(4);
+#undef FD_RH
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_resample_u8_vertical(const uint8_t* in, int64_t row_bytes, uint8_t* out, int32_t out_h, const int32_t* bounds,
+                                       const int32_t* taps, int32_t ksize, void* stream_) {
+  FD_REQUIRE(in && out && bounds && taps, "fd_resample_u8_vertical: null pointer");
+  FD_REQUIRE(row_bytes > 0 && out_h >= 0 && ksize > 0, "fd_resample_u8_vertical: bad shape");
+  if (out_h == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream_;
+  const bool vec = row_bytes % 4 == 0 && ((uintptr_t)in % 4 == 0) && ((uintptr_t)out % 4 == 0);
+  if (vec) resample_v_kernel<4><<<ew_grid(row_bytes / 4 * out_h), 256, 0, st>>>(in, (long long)row_bytes, out, out_h, bounds, taps, ksize);
+  else resample_v_kernel<1><<<ew_grid(row_bytes * out_h), 256, 0, st>>>(in, (long long)row_bytes, out, out_h, bounds, taps, ksize);
+  ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

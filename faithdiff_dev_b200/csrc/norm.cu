@@ -137,6 +137,202 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused GroupNorm(+SiLU): ONE persistent launch instead of partial / finalize / apply.
+//   The grid is every co-resident CTA slot of the GPU (occupancy x SMs), split into `nteams` teams.  A team walks over its
+//   samples; for each sample every member CTA (1) reduces its pixel chunk to per-group partial sums (same deterministic
+//   scheme as gn_partial_kernel), (2) arrives on the sample's counter; the LAST arriver combines the partials in fp64 in
+//   chunk order (deterministic whoever it is), writes the per-channel scale/shift table and releases the sample's ready
+//   flag; (3) members acquire the flag and stream y = silu(x*scale + shift) over the SAME pixel chunk, which they read a
+//   few microseconds earlier -> the second read is an L2 hit and DRAM sees one read + one write (4 B/elem).  The statistics
+//   of sample s+depth are computed before the wait on sample s, so the flag latency is covered by useful loads.
+//   Counters reset themselves (the last member past the wait clears them), so CUDA-graph replays need no memset node.
+//   Requires all CTAs co-resident: plain stream-ordered launch (never PDL), grid sized by the occupancy API.
+constexpr int kGnSyncMaxBatch = 64;
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8]) {
+  float2 t;
+  t = unpack_bf16(u.x); s[0] += t.x; q[0] += t.x * t.x; s[1] += t.y; q[1] += t.y * t.y;
+  t = unpack_bf16(u.y); s[2] += t.x; q[2] += t.x * t.x; s[3] += t.y; q[3] += t.y * t.y;
+  t = unpack_bf16(u.z); s[4] += t.x; q[4] += t.x * t.x; s[5] += t.y; q[5] += t.y * t.y;
+  t = unpack_bf16(u.w); s[6] += t.x; q[6] += t.x * t.x; s[7] += t.y; q[7] += t.y * t.y;
+}
+__device__ __forceinline__ uint4 norm8(const uint4& u, const float (&a)[8], const float (&b)[8], int silu) {
+  float f[8];
+  float2 t;
+  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], a[j], b[j]);
+  if (silu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+  }
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
+__global__ void __launch_bounds__(512, 2)
+gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, long long hw,
+                int groups, int R, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ partial, float* __restrict__ table,
+                unsigned* __restrict__ sync, int batch, int team_size, int nteams, int depth) {
+  extern __shared__ float sm[];
+  __shared__ float s_mean[64], s_rstd[64];
+  __shared__ int s_last;
+  const int team = blockIdx.x / team_size, m = blockIdx.x - team * team_size;
+  if (team >= nteams) return;
+  const int tid = threadIdx.x;
+  const int ct = c0 + c1, V = ct >> 3, cpg = ct / groups;
+  const int v = tid % V, r = tid / V;
+  const bool active = r < R;
+  const int ch = v * 8;
+  const bool from0 = ch < c0;
+  const int pitch = from0 ? c0 : c1;
+  const long long per = (hw + team_size - 1) / team_size;
+  const long long p0 = ((long long)m * per < hw) ? (long long)m * per : hw;
+  const long long p1 = (p0 + per < hw) ? p0 + per : hw;
+  unsigned* arrive = sync;
+  unsigned* ready = sync + kGnSyncMaxBatch;
+  unsigned* done = sync + 2 * kGnSyncMaxBatch;
+  const int nmine = (batch - team + nteams - 1) / nteams;            // samples team, team+nteams, ...
+
+  auto src_of = [&](int b) -> const __nv_bfloat16* {
+    return from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0);
+  };
+
+  auto stats = [&](int b) {
+    if (active) {
+      float s[8], q[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+      const __nv_bfloat16* src = src_of(b);
+      long long p = p0 + r;
+      for (; p + 3LL * R < p1; p += 4LL * R) {
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(src + p * pitch));
+        const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(src + (p + R) * pitch));
+        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(src + (p + 2LL * R) * pitch));
+        const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(src + (p + 3LL * R) * pitch));
+        acc8(u0, s, q); acc8(u1, s, q); acc8(u2, s, q); acc8(u3, s, q);
+      }
+      for (; p < p1; p += R) acc8(__ldg(reinterpret_cast<const uint4*>(src + p * pitch)), s, q);
+      float* ss = sm + (size_t)r * ct + ch;
+      float* sq = sm + (size_t)(R + r) * ct + ch;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ss[j] = s[j]; sq[j] = q[j]; }
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * ct; t += blockDim.x) {   // fold the R pixel rows of each (moment, channel) column into row 0
+      const int which = t >= ct, c = t - which * ct;
+      float* col = sm + (size_t)which * R * ct + c;
+      float acc = 0.f;
+      for (int rr = 0; rr < R; ++rr) acc += col[(size_t)rr * ct];
+      col[0] = acc;
+    }
+    __syncthreads();
+    for (int t = tid; t < 2 * groups; t += blockDim.x) {
+      const int g = t >> 1, which = t & 1;
+      const float* row = sm + (size_t)which * R * ct + g * cpg;
+      float acc = 0.f;
+      for (int c = 0; c < cpg; ++c) acc += row[c];
+      partial[(((long long)b * team_size + m) * groups + g) * 2 + which] = acc;
+      __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&arrive[b], 1u) == (unsigned)(team_size - 1));
+    __syncthreads();
+    if (s_last) {                                      // CTA-uniform: this CTA finalises sample b
+      __threadfence();
+      const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+      for (int g = warp; g < groups; g += nwarps) {
+        double s = 0.0, q = 0.0;
+        for (int c = lane; c < team_size; c += 32) {
+          const float2 pp = __ldcg(reinterpret_cast<const float2*>(partial + (((long long)b * team_size + c) * groups + g) * 2));
+          s += (double)pp.x;
+          q += (double)pp.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+          const double n = (double)hw * cpg;
+          const double mean = s / n;
+          double var = q / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          s_mean[g] = (float)mean;
+          s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
+      }
+      __syncthreads();
+      float* tb = table + (long long)b * 2 * ct;
+      for (int c = tid; c < ct; c += blockDim.x) {
+        const int g = c / cpg;
+        const float sc = s_rstd[g] * gamma[c];
+        tb[c] = sc;
+        tb[ct + c] = beta[c] - s_mean[g] * sc;
+      }
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_u32(&ready[b], 1u);
+    }
+  };
+
+  auto apply = [&](int b) {
+    if (tid == 0) {
+      const long long t0 = clock64();
+      while (ld_acquire_u32(&ready[b]) == 0u) {
+        __nanosleep(40);
+        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a member never arrived (not co-resident?) - fail, do not hang
+      }
+      if (atomicAdd(&done[b], 1u) == (unsigned)(team_size - 1)) {     // everyone is past the wait: recycle the counters
+        arrive[b] = 0u; ready[b] = 0u; done[b] = 0u;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const float* tb = table + (long long)b * 2 * ct + ch;
+      const float4 a0 = __ldcg(reinterpret_cast<const float4*>(tb)), a1 = __ldcg(reinterpret_cast<const float4*>(tb + 4));
+      const float4 b0 = __ldcg(reinterpret_cast<const float4*>(tb + ct)), b1 = __ldcg(reinterpret_cast<const float4*>(tb + ct + 4));
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float sft[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const __nv_bfloat16* src = src_of(b);
+      __nv_bfloat16* dst = out + (long long)b * hw * ct + ch;
+      long long p = p0 + r;
+      for (; p + 3LL * R < p1; p += 4LL * R) {
+        const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(src + p * pitch));
+        const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(src + (p + R) * pitch));
+        const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(src + (p + 2LL * R) * pitch));
+        const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(src + (p + 3LL * R) * pitch));
+        *reinterpret_cast<uint4*>(dst + p * ct) = norm8(u0, a, sft, silu);
+        *reinterpret_cast<uint4*>(dst + (p + R) * ct) = norm8(u1, a, sft, silu);
+        *reinterpret_cast<uint4*>(dst + (p + 2LL * R) * ct) = norm8(u2, a, sft, silu);
+        *reinterpret_cast<uint4*>(dst + (p + 3LL * R) * ct) = norm8(u3, a, sft, silu);
+      }
+      for (; p < p1; p += R)
+        *reinterpret_cast<uint4*>(dst + p * ct) = norm8(__ldcs(reinterpret_cast<const uint4*>(src + p * pitch)), a, sft, silu);
+    }
+  };
+
+  for (int i = 0; i < depth && i < nmine; ++i) stats(team + i * nteams);
+  for (int i = 0; i < nmine; ++i) {
+    apply(team + i * nteams);
+    if (i + depth < nmine) stats(team + (i + depth) * nteams);
+  }
+}
+
 // one warp per PAIR of rows (both rows' loads are issued before either reduction: twice the bytes in flight per warp);
 // cols <= 1280 (5 vectors of 8 per lane); single-pass sum / sum-of-squares in fp32 with a mean-shifted second moment
 template <int NV>
@@ -248,6 +444,58 @@ extern "C" int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int
                            (const __nv_bfloat16*)x1, c1, (long long)hw, total_vec, (const float*)scale, (const float*)shift, (int)silu,
                            (__nv_bfloat16*)out));
   g_launches += 3;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int64_t fd_groupnorm_sync_bytes() { return (int64_t)3 * kGnSyncMaxBatch * sizeof(unsigned); }
+
+static bool gn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("FD_GN_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma,
+                                       const float* beta, void* out, int32_t batch, int64_t hw, int32_t groups, float eps,
+                                       int32_t silu, float* work, void* sync, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x1) c1 = 0;
+  const int ct = c0 + c1;
+  FD_REQUIRE(x0 && out && work && gamma && beta, "fd_groupnorm_nhwc_fused: null pointer");
+  FD_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0 && ct % groups == 0 && groups <= 64, "fd_groupnorm_nhwc_fused: channels %d+%d groups %d unsupported", c0, c1, groups);
+  const int V = ct / 8;
+  int R = 512 / (V > 0 ? V : 1);
+  if (R < 1) R = 1;
+  const int threads = ((V * R + 31) / 32) * 32;
+  const size_t smem = (size_t)2 * R * ct * sizeof(float);
+  if (!sync || !gn_fused_enabled() || V > 512 || threads > 512 || batch > kGnSyncMaxBatch || smem > 48 * 1024 || hw < 1)
+    return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
+  // co-resident CTA slots (cached per launch shape)
+  static int occ_cache[17][13];                         // [threads/32][smem/4096]
+  int& occ = occ_cache[threads / 32][smem / 4096];
+  if (occ == 0) {
+    int o = 0;
+    FD_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, gn_fused_kernel, threads, smem));
+    occ = o < 1 ? -1 : (o > 2 ? 2 : o);
+  }
+  if (occ < 0) return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
+  int G = num_sms() * occ;
+  if (G > kGnMaxChunks) G = kGnMaxChunks;
+  const double sample_bytes = (double)hw * ct * 2.0;
+  int nteams = 1;
+  while (nteams * 2 <= batch && nteams * 2 <= 8 && nteams * 2 * 3.0 * sample_bytes <= 48e6 && G / (nteams * 2) >= 8) nteams *= 2;
+  const int team_size = G / nteams;
+  const int depth = (nteams * 3.0 * sample_bytes <= 64e6) ? 2 : 1;
+  float* partial = work;
+  float* table = work + (int64_t)batch * kGnMaxChunks * groups * 2;
+  gn_fused_kernel<<<dim3(team_size * nteams), dim3(threads), smem, stream>>>(
+      (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
+      (__nv_bfloat16*)out, partial, table, (unsigned*)sync, batch, team_size, nteams, depth);
+  ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -116,9 +116,24 @@ def groupnorm(x, gamma, beta, groups, eps, silu, x2=None, out=None):
     if out is None:
         out = torch.empty(x.shape[:-1] + (C0 + c1,), device=x.device, dtype=BF16)
     work = torch.empty(lib.fd_groupnorm_work_floats(B, groups, C0 + c1), device=x.device, dtype=torch.float32)
-    check(lib.fd_groupnorm_nhwc(_p(x), C0, _p(x2), c1, _p(gamma), _p(beta), _p(out), B, hw, groups, eps, int(silu),
-                                _p(work), _stream()), "fd_groupnorm_nhwc")
+    check(lib.fd_groupnorm_nhwc_fused(_p(x), C0, _p(x2), c1, _p(gamma), _p(beta), _p(out), B, hw, groups, eps, int(silu),
+                                      _p(work), _p(_gn_sync(x.device)), _stream()), "fd_groupnorm_nhwc_fused")
     return out
+
+
+_GN_SYNC = {}
+
+
+def _gn_sync(device):
+    """Per-device flag words of the one-launch GroupNorm: zeroed once, recycled by the kernel.  One buffer per device is
+    enough because the path issues GroupNorm on one stream at a time (graph capture, replay and eager calls are ordered);
+    two such kernels running CONCURRENTLY on one device are not supported.  Never allocated from a CUDA graph's private
+    pool: the first call must be eager (the tile-step warm-up before capture is), else the three-launch path is used."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _GN_SYNC.get(key)
+    if s is None and not torch.cuda.is_current_stream_capturing():
+        s = _GN_SYNC[key] = torch.zeros(lib.fd_groupnorm_sync_bytes() // 4, device=device, dtype=torch.int32)
+    return s
 
 
 def layernorm(x, gamma, beta, eps=1e-5, out=None):
@@ -312,6 +327,28 @@ def image_postprocess(x, nhwc_bf16=True):
         _, _, h, w = x.shape
     out = torch.empty((h, w, 3), device=x.device, dtype=torch.uint8)
     check(lib.fd_image_postprocess(_p(x), int(nhwc_bf16), _p(out), h, w, _stream()), "fd_image_postprocess")
+    return out
+
+
+def resample_u8_horizontal(img, bounds, taps, row0=0, rows=None):
+    """Horizontal pass of the PIL-compatible resample: u8 HWC device image -> [rows, out_w, C] over source rows
+    [row0, row0+rows).  bounds int32 [out_w,2], taps int32 [out_w,ksize] (image_process.resample_taps) on the device."""
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    H, W, Cc = img.shape
+    rows = H - row0 if rows is None else rows
+    assert 0 <= row0 and row0 + rows <= H
+    out = torch.empty((rows, bounds.shape[0], Cc), device=img.device, dtype=torch.uint8)
+    check(lib.fd_resample_u8_horizontal(_p(img[row0:]) if rows else _p(img), W, rows, _p(out), bounds.shape[0], Cc, _p(bounds),
+                                        _p(taps), taps.shape[1], _stream()), "fd_resample_u8_horizontal")
+    return out
+
+
+def resample_u8_vertical(img, bounds, taps):
+    """Vertical pass: u8 HWC device image -> [out_h, W, C]; bounds index the rows of `img`."""
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_contiguous()
+    out = torch.empty((bounds.shape[0], img.shape[1], img.shape[2]), device=img.device, dtype=torch.uint8)
+    check(lib.fd_resample_u8_vertical(_p(img), img.shape[1] * img.shape[2], _p(out), bounds.shape[0], _p(bounds), _p(taps),
+                                      taps.shape[1], _stream()), "fd_resample_u8_vertical")
     return out
 
 

@@ -91,6 +91,14 @@ int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups, int32_t channels
 int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
                       void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
                       void* stream);
+/* Same result from ONE persistent launch (per-sample arrive/ready flags in `sync`, second read of x from L2): the
+ * path the UNet / VAE use.  sync: fd_groupnorm_sync_bytes() bytes of device memory, zeroed ONCE by the caller and then
+ * left alone (the kernel recycles its counters); one buffer per stream that may run GroupNorm concurrently.  Falls back
+ * to the three-launch fd_groupnorm_nhwc for shapes it does not cover (or sync == NULL, or FD_GN_FUSED=0).          */
+int64_t fd_groupnorm_sync_bytes(void);
+int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
+                            void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
+                            void* sync, void* stream);
 /* LayerNorm over the last dim (affine), bf16 in/out. Replaces BasicTransformerBlock.norm1/2/3 and the
  * FaithDiff LayerNorm (…extension.py:229-235).                                                             */
 int fd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int32_t cols, float eps,
@@ -173,6 +181,16 @@ int fd_image_preprocess(const uint8_t* rgb_u8, void* out_nhwc_bf16, void* out_nc
                         void* stream);
 /* VaeImageProcessor.postprocess: NHWC bf16 (c=3) → u8 HWC: round(clamp(x/2+0.5,0,1)*255) (pipeline…:1451)   */
 int fd_image_postprocess(const void* x, int32_t x_is_nhwc_bf16, uint8_t* rgb_u8, int32_t h, int32_t w, void* stream);
+/* PIL-compatible separable resample of interleaved u8 images, bit-identical to Pillow's ImagingResample (8bpc):
+ * the caller's `image.resize((w*scale, h*scale), Image.LANCZOS)` (test_wo_llava.py:78-81, test.py:104-108) without the
+ * host round trip.  Two passes with a u8 intermediate, exactly as Pillow orders them (horizontal over the source rows
+ * the vertical pass needs, then vertical).  bounds: int32 [out, 2] = (first source index, tap count); taps: int32
+ * [out, ksize] 22-bit fixed point — both from the host (faithdiff_dev_b200.image_process.resample_taps).
+ * horizontal: in [rows, in_w, channels] -> out [rows, out_w, channels]; vertical: in [*, row_bytes] -> out [out_h, row_bytes]. */
+int fd_resample_u8_horizontal(const uint8_t* in, int32_t in_w, int64_t rows, uint8_t* out, int32_t out_w, int32_t channels,
+                              const int32_t* bounds, const int32_t* taps, int32_t ksize, void* stream);
+int fd_resample_u8_vertical(const uint8_t* in, int64_t row_bytes, uint8_t* out, int32_t out_h, const int32_t* bounds,
+                            const int32_t* taps, int32_t ksize, void* stream);
 /* utils/color_fix.py:14-27 adain_color_fix and :29-42 wavelet_color_fix on u8 HWC images (fp32 math).
  * work: fp32 scratch of fd_colorfix_work_floats(h, w) elements.                                              */
 int64_t fd_colorfix_work_floats(int32_t h, int32_t w);

@@ -187,3 +187,59 @@ def test_text_encoder_host_logic():
         CLIPTextEncoder(hidden_size=640, num_attention_heads=8)     # 80-wide heads: not this kernel
     with pytest.raises(RuntimeError):
         CLIPTextEncoder()(ids)                                      # weights not loaded
+
+
+def _np_resample(a, ow, oh):
+    """The two integer passes of fd_resample_u8_* in numpy (checker only), fed by the product's tap tables."""
+    from faithdiff_dev_b200.image_process import resample_taps
+    H, W, _ = a.shape
+
+    def clip8(v):
+        return np.clip(v >> 22, 0, 255).astype(np.uint8)
+    row0 = 0
+    if ow != W:
+        hb, hk = resample_taps(W, ow)
+        rows = a
+        if oh != H:
+            vb, _ = resample_taps(H, oh)
+            row0 = int(vb[0, 0])
+            rows = a[row0:int(vb[-1, 0] + vb[-1, 1])]
+        tmp = np.empty((rows.shape[0], ow, a.shape[2]), np.uint8)
+        for xx in range(ow):
+            x0, n = hb[xx]
+            tmp[:, xx] = clip8((rows[:, x0:x0 + n].astype(np.int64) * hk[xx, :n].astype(np.int64)[None, :, None]).sum(1) + (1 << 21))
+        a = tmp
+    if oh != H:
+        vb, vk = resample_taps(H, oh)
+        out = np.empty((oh,) + a.shape[1:], np.uint8)
+        for yy in range(oh):
+            y0, n = vb[yy]
+            y0 -= row0
+            out[yy] = clip8((a[y0:y0 + n].astype(np.int64) * vk[yy, :n].astype(np.int64)[:, None, None]).sum(0) + (1 << 21))
+        a = out
+    return a
+
+
+@pytest.mark.parametrize("w,h,ow,oh", [(37, 23, 74, 46), (64, 48, 128, 96), (50, 40, 200, 160), (100, 80, 50, 40), (33, 17, 40, 17),
+                                       (31, 29, 31, 60), (120, 90, 37, 29), (16, 16, 129, 67), (240, 135, 480, 270)])
+def test_lanczos_tap_tables_reproduce_pil(w, h, ow, oh):
+    """The caller's `image.resize(..., Image.LANCZOS)` (test_wo_llava.py:81): the product's host-side tap tables pushed
+    through the kernels' integer arithmetic are bit-identical to Pillow — up-, down- and one-axis scaling."""
+    from PIL import Image
+    a = np.random.default_rng(w * 1000 + oh).integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(a).resize((ow, oh), Image.LANCZOS))
+    assert np.array_equal(_np_resample(a, ow, oh), ref)
+
+
+def test_lanczos_tap_table_properties():
+    from faithdiff_dev_b200.image_process import resample_taps, resize_lanczos
+    for n_in, n_out in [(1920, 3840), (1080, 2160), (512, 2048), (2048, 512), (7, 7)]:
+        b, k = resample_taps(n_in, n_out)
+        assert b.shape == (n_out, 2) and k.shape[0] == n_out and k.dtype == np.int32
+        assert (b[:, 0] >= 0).all() and (b[:, 0] + b[:, 1] <= n_in).all() and (b[:, 1] <= k.shape[1]).all()
+        assert (np.abs(k.sum(1) - (1 << 22)) <= k.shape[1]).all()              # taps are normalised before rounding
+        assert (np.diff(b[:, 0]) >= 0).all()
+    with pytest.raises(RuntimeError):
+        resize_lanczos(np.zeros((8, 8, 3), np.uint8), (16, 16), device="cpu")   # no CPU path
+    with pytest.raises(ValueError):
+        resize_lanczos(np.zeros((8, 8, 3), np.float32), (16, 16))
