@@ -191,16 +191,36 @@ def roofline_pass(pipe, torch, ops):
         s.record(); r = orig_conv(x, w, *args, **kw); e.record()
         rec.append((s, e, 2.0 * r.numel() * w.shape[1]))
         return r
-    O.gemm, O.conv3x3 = gemm, conv
+    # the HBM-bound kernels of the same pass: algorithmic bytes = read + write of the bf16 tensor (4 B / element)
+    hbm = {"groupnorm": [], "layernorm": []}
+    orig_gn, orig_ln = O.groupnorm, O.layernorm
+
+    def groupnorm(x, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); r = orig_gn(x, *args, **kw); e.record()
+        hbm["groupnorm"].append((s, e, 4.0 * r.numel()))
+        return r
+
+    def layernorm(x, *args, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); r = orig_ln(x, *args, **kw); e.record()
+        hbm["layernorm"].append((s, e, 4.0 * r.numel()))
+        return r
+    O.gemm, O.conv3x3, O.groupnorm, O.layernorm = gemm, conv, groupnorm, layernorm
     try:
         torch.cuda._sleep(int(2e8))                # ~0.1 s head start for the host
         ts._run()
         torch.cuda.synchronize()
     finally:
-        O.gemm, O.conv3x3 = orig_gemm, orig_conv
+        O.gemm, O.conv3x3, O.groupnorm, O.layernorm = orig_gemm, orig_conv, orig_gn, orig_ln
     dur = sum(s.elapsed_time(e) for s, e, _ in rec) * 1e-3
     flops = sum(f for _, _, f in rec)
-    return {"launches": len(rec), "seconds": dur, "flops": flops, "tiles": ts.ns / 2.0}
+    hbm_out = {}
+    for name, lst in hbm.items():
+        if lst:
+            sec = sum(s.elapsed_time(e) for s, e, _ in lst) * 1e-3
+            hbm_out[name] = {"launches": len(lst), "seconds": sec, "bytes": sum(b for _, _, b in lst)}
+    return {"launches": len(rec), "seconds": dur, "flops": flops, "tiles": ts.ns / 2.0, "hbm": hbm_out}
 
 
 def main():
@@ -306,6 +326,7 @@ def main():
     value, e2e = args.steps * mp / (ms * 1e-3), args.steps * mp / (ms_e2e * 1e-3)
 
     roof = None
+    roof_hbm = None
     cpu = None
     if rank == 0:
         peaks = {}
@@ -333,6 +354,18 @@ def main():
                     "unet_tile_step_ms": stage["denoise"] / wl["steps"] / max(1, len(pipe.tlc_vae_latents.idxes)) * world,
                     "path_tflops_vs_reference_algorithm": TILE_STEP_TFLOP_128 * len(pipe.tlc_vae_latents.idxes) * wl["steps"]
                     / (stage["denoise"] * 1e-3) / world}
+            hbm_peak, hbm_which = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else \
+                (6400.0, "fallback (B200_PROFILING.md)")
+            roof_hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_which,
+                        "how": "same instrumented pass: algorithmic bytes (bf16 read + write, 4 B/element) of every GroupNorm / LayerNorm "
+                               "call of the UNet evaluation / summed CUDA-event durations (one launch per call)",
+                        "kernels": {}}
+            for name, kern in (("groupnorm", "gn_fused_kernel"), ("layernorm", "layernorm_bulk_kernel")):
+                h = r["hbm"].get(name)
+                if h:
+                    a = h["bytes"] / h["seconds"] / 1e9
+                    roof_hbm["kernels"][kern] = {"achieved": a, "frac": a / hbm_peak, "launches": h["launches"],
+                                                 "avg_launch_us": h["seconds"] / h["launches"] * 1e6}
         if world == 1 and not args.no_cpu_baseline:
             once = cpu_tile_step_seconds(64)
             once()
@@ -354,7 +387,7 @@ def main():
                        "stage_ms_last_step": {k: round(v, 1) for k, v in stage.items()}},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(host_out.numel()),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu}))
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu}))
     if world > 1:
         torch.distributed.destroy_process_group()
 

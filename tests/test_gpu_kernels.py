@@ -172,7 +172,8 @@ def test_groupnorm_one_launch_matches_three_launch(ops, B, HW, C0, C1, silu):
         assert torch.equal(dst, out)
 
 
-@pytest.mark.parametrize("rows,cols", [(8192, 640), (2048, 1280), (100, 128)])
+@pytest.mark.parametrize("rows,cols", [(8192, 640), (2048, 1280), (100, 128), (1031, 1280), (4099, 320), (3000, 768), (28672, 1280),
+                                       (1024, 8), (65536, 640)])
 def test_layernorm(ops, rows, cols):
     torch.manual_seed(5)
     x = (torch.randn(rows, cols, device="cuda") * 3 + 1).to(BF)
