@@ -33,9 +33,31 @@ def workload(name):
                          "encoder + tiled VAE, start_point=lr, adain colour fix", lq=(1920, 1080), scale=2, steps=20)
     if name == "1k":
         return dict(name="cfg2: 512x512 -> 1024x1024 2x SR, 20 steps, 1 tile", lq=(512, 512), scale=2, steps=20)
+    if name == "batch32":
+        return dict(name="cfg5: batch of 32 x (512x512 -> 2048x2048 4x SR), 20 steps, 9 tiles per image, images data-parallel "
+                         "across ranks (no exchange)", lq=(512, 512), scale=4, steps=20, images=32)
     if name == "tiny":
         return dict(name="dev: 256x256 -> 512x512, 2 steps", lq=(256, 256), scale=2, steps=2)
     raise SystemExit("unknown workload " + name)
+
+
+def count_tiles(wl, k=128, overlap=0.5):
+    """Number of latent tiles of the workload (the walk of LocalAttention.grids, pipeline_FaithDiff_tlc.py:172-204: step
+    ceil(k*overlap), last tile clamped to dim-k), for scaling the CPU sample; the CUDA arm reports the pipeline's own count."""
+    import math
+    n = 1
+    for dim in (wl["lq"][1] * wl["scale"] // 8, wl["lq"][0] * wl["scale"] // 8):
+        kk = min(k, dim)
+        if (dim - 1) // kk + 1 == 1:
+            continue
+        step, pos, cnt = math.ceil(kk * overlap), 0, 0
+        while True:
+            cnt += 1
+            if pos + kk >= dim:
+                break
+            pos += step
+        n *= cnt
+    return n
 
 
 def synthetic_lq(w, h, seed=0):
@@ -153,9 +175,10 @@ def reference_arm(args, wl):
     t = [once() for _ in range(args.steps)]
     per = sum(t) / len(t)
     W, H = wl["lq"][0] * wl["scale"], wl["lq"][1] * wl["scale"]
-    tiles = 28 if wl["lq"] == (1920, 1080) else 1
+    n_images = args.images or wl.get("images", 1)
+    tiles = count_tiles(wl) * n_images
     full = per * (TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64) * tiles * wl["steps"]
-    val = W * H / 1e6 / full
+    val = W * H / 1e6 * n_images / full
     sample = ("1 UNet tile-step (CFG batch 2, 64x64 latent, fp32 torch on %d threads) = %.2f s; scaled by algorithmic FLOPs "
               "x%.2f to a 128x128 tile and x%d tile-steps (LQ encoder / VAE / blend time not charged to the CPU)"
               % (os.cpu_count(), per, TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64, tiles * wl["steps"]))
@@ -232,6 +255,9 @@ def main():
     ap.add_argument("--workload", default="4k")
     ap.add_argument("--tiles-per-launch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--images", type=int, default=None, help="batch workloads: number of images (default: the workload's)")
+    ap.add_argument("--fp8", action="store_true", help="the reference's fp8 mode: UNet weights rounded through e4m3 (storage "
+                                                       "only, utils/system.py:13-32); compute stays bf16")
     args = ap.parse_args()
     wl = workload(args.workload)
     if args.impl == "reference":
@@ -253,7 +279,12 @@ def main():
     from faithdiff_dev_b200.color_fix import color_fix_u8
 
     unet = fd.UNet2DConditionModel(**arch.SDXL_UNET_CONFIG)
-    unet.load_state_dict(arch.random_state_dict(arch.unet_param_shapes(arch.SDXL_UNET_CONFIG), seed=1234))
+    sd = arch.random_state_dict(arch.unet_param_shapes(arch.SDXL_UNET_CONFIG), seed=1234)
+    if args.fp8:
+        from faithdiff_dev_b200.create_model import quantize_8bit_state_dict
+        sd = quantize_8bit_state_dict(sd)
+    unet.load_state_dict(sd)
+    del sd
     vae = fd.AutoencoderKL(**arch.SDXL_VAE_CONFIG)
     vae.load_state_dict(arch.random_state_dict(arch.vae_param_shapes(), seed=4321))
     pipe = fd.FaithDiffStableDiffusionXLPipeline(vae, unet.denoise_encoder, None, None, None, None, unet,
@@ -261,7 +292,12 @@ def main():
     pipe.set_encoder_tile_settings()
     pipe.enable_vae_tiling()
     pipe.tiles_per_launch = args.tiles_per_launch
-    if world > 1:
+    n_images = args.images or wl.get("images", 1)
+    batch_mode = "images" in wl
+    if batch_mode:                               # cfg5: whole images per rank, single-GPU pipeline on each
+        from faithdiff_dev_b200.dist import shard_images
+        my_images = shard_images(n_images, rank, world)
+    elif world > 1:
         pipe.set_distributed(rank, world)
 
     # synthetic input exactly as test_wo_llava.py:78-82 prepares it: LANCZOS upscale of the LQ image, pad to x8
@@ -275,7 +311,7 @@ def main():
     g = torch.Generator().manual_seed(7)
     pe, npe = torch.randn(1, 77, 2048, generator=g).cuda(), torch.randn(1, 77, 2048, generator=g).cuda()
     pp, npp = torch.randn(1, 1280, generator=g).cuda(), torch.randn(1, 1280, generator=g).cuda()
-    mp = W * H / 1e6
+    mp = W * H / 1e6 * n_images
 
     def restore(img, seed=42):
         torch.manual_seed(seed)
@@ -286,12 +322,15 @@ def main():
         return out
 
     def step_device():                       # inputs already resident in HBM
+        if batch_mode:
+            return [color_fix_u8(restore(dev_u8, seed=42 + i), dev_u8, "adain") for i in my_images]
         return color_fix_u8(restore(dev_u8), dev_u8, "adain")
 
     def step_host():                         # the call a user makes: host image in, host image out
-        out = restore(host_u8)               # H2D of the pinned u8 image happens inside (pipeline._preprocess)
-        fixed = color_fix_u8(out, pipe._last_input_u8, "adain")
-        host_out.copy_(fixed, non_blocking=True)
+        for i in (my_images if batch_mode else [0]):
+            out = restore(host_u8, seed=42 + i)  # H2D of the pinned u8 image happens inside (pipeline._preprocess)
+            fixed = color_fix_u8(out, pipe._last_input_u8, "adain")
+            host_out.copy_(fixed, non_blocking=True)
         return fixed
 
     def barrier():
@@ -370,7 +409,7 @@ def main():
             once = cpu_tile_step_seconds(64)
             once()
             t = once()
-            tiles = len(pipe.tlc_vae_latents.idxes)
+            tiles = len(pipe.tlc_vae_latents.idxes) * n_images
             full = t * (TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64) * tiles * wl["steps"]
             cpu = {"value": mp / full, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                    "sample": "1 UNet tile-step (CFG batch 2, 64x64 latent, fp32 oracle on %d threads) = %.2f s, scaled by "
@@ -378,14 +417,17 @@ def main():
                              % (os.cpu_count(), t, TILE_STEP_TFLOP_128 / TILE_STEP_TFLOP_64, tiles * wl["steps"])}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 (UNet weights rounded through e4m3)" if args.fp8 else "bf16",
             "data": "synthetic",
             "config": {"workload": wl["name"], "tiles": len(pipe.tlc_vae_latents.idxes), "tiles_per_launch": args.tiles_per_launch,
-                       "parallelism": "%d GPU(s): (tile, CFG-branch) units in contiguous balanced ranges, one NCCL all-reduce of the fp32 canvas "
-                                      "per scheduler step; tiled LQ-encoder/VAE tiles round-robin + broadcast" % world,
+                       "parallelism": ("%d GPU(s): %d whole images per rank (contiguous ranges), no exchange" % (world, len(my_images)))
+                       if batch_mode else
+                       "%d GPU(s): (tile, CFG-branch) units in contiguous balanced ranges, one NCCL all-reduce of the fp32 canvas "
+                       "per scheduler step; tiled LQ-encoder/VAE tiles round-robin + broadcast" % world,
                        "l2": "no explicit flush: each step streams 5.3 GB of weights 280x plus activations (>> 126 MB L2)",
                        "stage_ms_last_step": {k: round(v, 1) for k, v in stage.items()}},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()), "d2h_bytes_per_step": int(host_out.numel()),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(host_u8.numel()) * n_images, "d2h_bytes_per_step": int(host_out.numel()) * n_images,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu}))
     if world > 1:

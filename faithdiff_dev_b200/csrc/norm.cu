@@ -138,15 +138,16 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Fused GroupNorm(+SiLU): ONE persistent launch instead of partial / finalize / apply.
-//   The grid is every co-resident CTA slot of the GPU (occupancy x SMs), split into `nteams` teams.  A team walks over its
-//   samples; for each sample every member CTA (1) reduces its pixel chunk to per-group partial sums (same deterministic
-//   scheme as gn_partial_kernel), (2) arrives on the sample's counter; the LAST arriver combines the partials in fp64 in
-//   chunk order (deterministic whoever it is), writes the per-channel scale/shift table and releases the sample's ready
-//   flag; (3) members acquire the flag and stream y = silu(x*scale + shift) over the SAME pixel chunk, which they read a
-//   few microseconds earlier -> the second read is an L2 hit and DRAM sees one read + one write (4 B/elem).  The statistics
-//   of sample s+depth are computed before the wait on sample s, so the flag latency is covered by useful loads.
-//   Counters reset themselves (the last member past the wait clears them), so CUDA-graph replays need no memset node.
+// Fused GroupNorm(+SiLU): ONE launch instead of partial / finalize / apply.
+//   The grid is the GPU's co-resident CTA slots (occupancy x SMs).  Each CTA owns ONE pixel chunk of ONE sample:
+//   (1) it reduces the chunk to per-group partial sums (the deterministic scheme of gn_partial_kernel, four 16-byte loads in
+//   flight per thread) and arrives on the sample's counter; (2) the LAST arriver of a sample combines the partials in fp64 in
+//   chunk order (deterministic whoever it is), writes the per-channel scale/shift table and releases the sample's ready flag;
+//   (3) every CTA acquires its sample's flag and streams y = silu(x*scale + shift) over its own chunk BACKWARDS, so the pixels
+//   it read last — the ones most likely still in L2 — are re-read first.  All loads of the statistics pass are issued before
+//   the first store of the apply pass: the fence before the arrive never has a store stream to wait for (a first version that
+//   interleaved per-sample statistics with the apply stores of the previous sample spent its time in those fences).
+//   Counters reset themselves (the last CTA past the wait clears them), so CUDA-graph replays need no memset node.
 //   Requires all CTAs co-resident: plain stream-ordered launch (never PDL), grid sized by the occupancy API.
 constexpr int kGnSyncMaxBatch = 64;
 
@@ -160,10 +161,10 @@ __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
 }
 __device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8]) {
   float2 t;
-  t = unpack_bf16(u.x); s[0] += t.x; q[0] += t.x * t.x; s[1] += t.y; q[1] += t.y * t.y;
-  t = unpack_bf16(u.y); s[2] += t.x; q[2] += t.x * t.x; s[3] += t.y; q[3] += t.y * t.y;
-  t = unpack_bf16(u.z); s[4] += t.x; q[4] += t.x * t.x; s[5] += t.y; q[5] += t.y * t.y;
-  t = unpack_bf16(u.w); s[6] += t.x; q[6] += t.x * t.x; s[7] += t.y; q[7] += t.y * t.y;
+  t = unpack_bf16(u.x); s[0] += t.x; q[0] = fmaf(t.x, t.x, q[0]); s[1] += t.y; q[1] = fmaf(t.y, t.y, q[1]);
+  t = unpack_bf16(u.y); s[2] += t.x; q[2] = fmaf(t.x, t.x, q[2]); s[3] += t.y; q[3] = fmaf(t.y, t.y, q[3]);
+  t = unpack_bf16(u.z); s[4] += t.x; q[4] = fmaf(t.x, t.x, q[4]); s[5] += t.y; q[5] = fmaf(t.y, t.y, q[5]);
+  t = unpack_bf16(u.w); s[6] += t.x; q[6] = fmaf(t.x, t.x, q[6]); s[7] += t.y; q[7] = fmaf(t.y, t.y, q[7]);
 }
 __device__ __forceinline__ uint4 norm8(const uint4& u, const float (&a)[8], const float (&b)[8], int silu) {
   float f[8];
@@ -187,12 +188,12 @@ __global__ void __launch_bounds__(512, 2)
 gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, long long hw,
                 int groups, int R, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ partial, float* __restrict__ table,
-                unsigned* __restrict__ sync, int batch, int team_size, int nteams, int depth) {
+                unsigned* __restrict__ sync, int batch, int cps) {
   extern __shared__ float sm[];
   __shared__ float s_mean[64], s_rstd[64];
   __shared__ int s_last;
-  const int team = blockIdx.x / team_size, m = blockIdx.x - team * team_size;
-  if (team >= nteams) return;
+  const int b = blockIdx.x / cps, m = blockIdx.x - b * cps;     // sample, chunk of the sample
+  if (b >= batch) return;
   const int tid = threadIdx.x;
   const int ct = c0 + c1, V = ct >> 3, cpg = ct / groups;
   const int v = tid % V, r = tid / V;
@@ -200,136 +201,134 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
   const int ch = v * 8;
   const bool from0 = ch < c0;
   const int pitch = from0 ? c0 : c1;
-  const long long per = (hw + team_size - 1) / team_size;
+  const long long per = (hw + cps - 1) / cps;
   const long long p0 = ((long long)m * per < hw) ? (long long)m * per : hw;
   const long long p1 = (p0 + per < hw) ? p0 + per : hw;
-  unsigned* arrive = sync;
-  unsigned* ready = sync + kGnSyncMaxBatch;
-  unsigned* done = sync + 2 * kGnSyncMaxBatch;
-  const int nmine = (batch - team + nteams - 1) / nteams;            // samples team, team+nteams, ...
+  unsigned* arrive = sync + b;
+  unsigned* ready = sync + kGnSyncMaxBatch + b;
+  unsigned* done = sync + 2 * kGnSyncMaxBatch + b;
+  const __nv_bfloat16* src = from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0);
+  // pixels of this thread: p0 + r + k*R, k in [0, n)
+  const long long n = (active && p0 + r < p1) ? (p1 - p0 - r + R - 1) / R : 0;
+  const long long stride = (long long)R * pitch;
 
-  auto src_of = [&](int b) -> const __nv_bfloat16* {
-    return from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0);
-  };
-
-  auto stats = [&](int b) {
-    if (active) {
-      float s[8], q[8];
+  // ---- (1) statistics of the chunk
+  {
+    float s[8], q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-      const __nv_bfloat16* src = src_of(b);
-      long long p = p0 + r;
-      for (; p + 3LL * R < p1; p += 4LL * R) {
-        const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(src + p * pitch));
-        const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(src + (p + R) * pitch));
-        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(src + (p + 2LL * R) * pitch));
-        const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(src + (p + 3LL * R) * pitch));
-        acc8(u0, s, q); acc8(u1, s, q); acc8(u2, s, q); acc8(u3, s, q);
-      }
-      for (; p < p1; p += R) acc8(__ldg(reinterpret_cast<const uint4*>(src + p * pitch)), s, q);
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const __nv_bfloat16* ptr = src + (p0 + r) * pitch;
+    long long k = 0;
+    for (; k + 4 <= n; k += 4) {
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(ptr));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(ptr + stride));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(ptr + 2 * stride));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(ptr + 3 * stride));
+      ptr += 4 * stride;
+      acc8(u0, s, q); acc8(u1, s, q); acc8(u2, s, q); acc8(u3, s, q);
+    }
+    for (; k < n; ++k, ptr += stride) acc8(__ldg(reinterpret_cast<const uint4*>(ptr)), s, q);
+    if (active) {
       float* ss = sm + (size_t)r * ct + ch;
       float* sq = sm + (size_t)(R + r) * ct + ch;
 #pragma unroll
       for (int j = 0; j < 8; ++j) { ss[j] = s[j]; sq[j] = q[j]; }
     }
-    __syncthreads();
-    for (int t = tid; t < 2 * ct; t += blockDim.x) {   // fold the R pixel rows of each (moment, channel) column into row 0
-      const int which = t >= ct, c = t - which * ct;
-      float* col = sm + (size_t)which * R * ct + c;
-      float acc = 0.f;
-      for (int rr = 0; rr < R; ++rr) acc += col[(size_t)rr * ct];
-      col[0] = acc;
-    }
-    __syncthreads();
-    for (int t = tid; t < 2 * groups; t += blockDim.x) {
-      const int g = t >> 1, which = t & 1;
-      const float* row = sm + (size_t)which * R * ct + g * cpg;
-      float acc = 0.f;
-      for (int c = 0; c < cpg; ++c) acc += row[c];
-      partial[(((long long)b * team_size + m) * groups + g) * 2 + which] = acc;
-      __threadfence();
-    }
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(&arrive[b], 1u) == (unsigned)(team_size - 1));
-    __syncthreads();
-    if (s_last) {                                      // CTA-uniform: this CTA finalises sample b
-      __threadfence();
-      const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-      for (int g = warp; g < groups; g += nwarps) {
-        double s = 0.0, q = 0.0;
-        for (int c = lane; c < team_size; c += 32) {
-          const float2 pp = __ldcg(reinterpret_cast<const float2*>(partial + (((long long)b * team_size + c) * groups + g) * 2));
-          s += (double)pp.x;
-          q += (double)pp.y;
-        }
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * ct; t += blockDim.x) {   // fold the R pixel rows of each (moment, channel) column into row 0
+    const int which = t >= ct, c = t - which * ct;
+    float* col = sm + (size_t)which * R * ct + c;
+    float acc = 0.f;
+    for (int rr = 0; rr < R; ++rr) acc += col[(size_t)rr * ct];
+    col[0] = acc;
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * groups; t += blockDim.x) {
+    const int g = t >> 1, which = t & 1;
+    const float* row = sm + (size_t)which * R * ct + g * cpg;
+    float acc = 0.f;
+    for (int c = 0; c < cpg; ++c) acc += row[c];
+    partial[(((long long)b * cps + m) * groups + g) * 2 + which] = acc;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(arrive, 1u) == (unsigned)(cps - 1));
+  __syncthreads();
+
+  // ---- (2) the last arriver of the sample finalises it
+  if (s_last) {                                      // CTA-uniform
+    __threadfence();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int g = warp; g < groups; g += nwarps) {
+      double s = 0.0, q = 0.0;
+      for (int c = lane; c < cps; c += 32) {
+        const float2 pp = __ldcg(reinterpret_cast<const float2*>(partial + (((long long)b * cps + c) * groups + g) * 2));
+        s += (double)pp.x;
+        q += (double)pp.y;
+      }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (lane == 0) {
-          const double n = (double)hw * cpg;
-          const double mean = s / n;
-          double var = q / n - mean * mean;
-          if (var < 0.0) var = 0.0;
-          s_mean[g] = (float)mean;
-          s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
-        }
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
       }
-      __syncthreads();
-      float* tb = table + (long long)b * 2 * ct;
-      for (int c = tid; c < ct; c += blockDim.x) {
-        const int g = c / cpg;
-        const float sc = s_rstd[g] * gamma[c];
-        tb[c] = sc;
-        tb[ct + c] = beta[c] - s_mean[g] * sc;
-      }
-      __threadfence();
-      __syncthreads();
-      if (tid == 0) st_release_u32(&ready[b], 1u);
-    }
-  };
-
-  auto apply = [&](int b) {
-    if (tid == 0) {
-      const long long t0 = clock64();
-      while (ld_acquire_u32(&ready[b]) == 0u) {
-        __nanosleep(40);
-        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a member never arrived (not co-resident?) - fail, do not hang
-      }
-      if (atomicAdd(&done[b], 1u) == (unsigned)(team_size - 1)) {     // everyone is past the wait: recycle the counters
-        arrive[b] = 0u; ready[b] = 0u; done[b] = 0u;
+      if (lane == 0) {
+        const double cnt = (double)hw * cpg;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)mean;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
       }
     }
     __syncthreads();
-    if (active) {
-      const float* tb = table + (long long)b * 2 * ct + ch;
-      const float4 a0 = __ldcg(reinterpret_cast<const float4*>(tb)), a1 = __ldcg(reinterpret_cast<const float4*>(tb + 4));
-      const float4 b0 = __ldcg(reinterpret_cast<const float4*>(tb + ct)), b1 = __ldcg(reinterpret_cast<const float4*>(tb + ct + 4));
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float sft[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const __nv_bfloat16* src = src_of(b);
-      __nv_bfloat16* dst = out + (long long)b * hw * ct + ch;
-      long long p = p0 + r;
-      for (; p + 3LL * R < p1; p += 4LL * R) {
-        const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(src + p * pitch));
-        const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(src + (p + R) * pitch));
-        const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(src + (p + 2LL * R) * pitch));
-        const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(src + (p + 3LL * R) * pitch));
-        *reinterpret_cast<uint4*>(dst + p * ct) = norm8(u0, a, sft, silu);
-        *reinterpret_cast<uint4*>(dst + (p + R) * ct) = norm8(u1, a, sft, silu);
-        *reinterpret_cast<uint4*>(dst + (p + 2LL * R) * ct) = norm8(u2, a, sft, silu);
-        *reinterpret_cast<uint4*>(dst + (p + 3LL * R) * ct) = norm8(u3, a, sft, silu);
-      }
-      for (; p < p1; p += R)
-        *reinterpret_cast<uint4*>(dst + p * ct) = norm8(__ldcs(reinterpret_cast<const uint4*>(src + p * pitch)), a, sft, silu);
+    float* tb = table + (long long)b * 2 * ct;
+    for (int c = tid; c < ct; c += blockDim.x) {
+      const int g = c / cpg;
+      const float sc = s_rstd[g] * gamma[c];
+      tb[c] = sc;
+      tb[ct + c] = beta[c] - s_mean[g] * sc;
     }
-  };
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_u32(ready, 1u);
+  }
 
-  for (int i = 0; i < depth && i < nmine; ++i) stats(team + i * nteams);
-  for (int i = 0; i < nmine; ++i) {
-    apply(team + i * nteams);
-    if (i + depth < nmine) stats(team + (i + depth) * nteams);
+  // ---- (3) wait for the sample's table, then normalise the chunk back to front
+  if (tid == 0) {
+    const long long t0 = clock64();
+    while (ld_acquire_u32(ready) == 0u) {
+      __nanosleep(32);
+      if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a CTA of the sample never arrived (not co-resident?) - fail, do not hang
+    }
+    if (atomicAdd(done, 1u) == (unsigned)(cps - 1)) {   // every CTA of the sample is past the wait: recycle its counters
+      *arrive = 0u; *ready = 0u; *done = 0u;
+    }
+  }
+  __syncthreads();
+  if (n > 0) {
+    const float* tb = table + (long long)b * 2 * ct + ch;
+    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(tb)), a1 = __ldcg(reinterpret_cast<const float4*>(tb + 4));
+    const float4 b0 = __ldcg(reinterpret_cast<const float4*>(tb + ct)), b1 = __ldcg(reinterpret_cast<const float4*>(tb + ct + 4));
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float sft[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const long long ostride = (long long)R * ct;
+    const __nv_bfloat16* ptr = src + (p0 + r + (n - 1) * R) * pitch;
+    __nv_bfloat16* dst = out + ((long long)b * hw + p0 + r + (n - 1) * R) * ct + ch;
+    long long k = 0;
+    for (; k + 4 <= n; k += 4) {
+      const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(ptr));
+      const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(ptr - stride));
+      const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(ptr - 2 * stride));
+      const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(ptr - 3 * stride));
+      *reinterpret_cast<uint4*>(dst) = norm8(u0, a, sft, silu);
+      *reinterpret_cast<uint4*>(dst - ostride) = norm8(u1, a, sft, silu);
+      *reinterpret_cast<uint4*>(dst - 2 * ostride) = norm8(u2, a, sft, silu);
+      *reinterpret_cast<uint4*>(dst - 3 * ostride) = norm8(u3, a, sft, silu);
+      ptr -= 4 * stride;
+      dst -= 4 * ostride;
+    }
+    for (; k < n; ++k, ptr -= stride, dst -= ostride) *reinterpret_cast<uint4*>(dst) = norm8(__ldcs(reinterpret_cast<const uint4*>(ptr)), a, sft, silu);
   }
 }
 
@@ -404,12 +403,13 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   }
 }
 // ---------------------------------------------------------------------------------------------------------------------
-// LayerNorm, persistent + bulk-copy pipelined.  A producer thread streams blocks of 16 contiguous rows into a 4-stage
+// LayerNorm, persistent + bulk-copy pipelined.  A producer thread streams blocks of 16 contiguous rows into a 5-stage
 // shared-memory ring with ONE cp.async.bulk each (the rows of a block are contiguous in memory) completing on an mbarrier;
-// eight consumer warps take two rows each from the ring, so the loads of the next three blocks are always in flight while a
+// sixteen consumer warps take one row each from the ring, so the loads of the next four blocks are always in flight while a
 // block is reduced.  The arithmetic is packed fp32x2 (add/fma.f32x2): at HBM speed an SM has to retire ~11 elements per clock,
 // and the scalar version (7.5 lane-instructions per element) sat at two thirds of the issue rate by itself.
-constexpr int kLnStages = 4, kLnWarps = 8, kLnBlockRows = 16;
+// (A first version with 8 consumer warps x 2 rows was latency-bound: 13 % of the warp slots active, 3.1 TB/s.)
+constexpr int kLnStages = 5, kLnWarps = 16, kLnBlockRows = 16;
 
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
@@ -464,47 +464,35 @@ layernorm_bulk_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
   for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
     const int s = it % kLnStages;
     mbar_wait(&full[s], (it / kLnStages) & 1);
-    const long long r0 = blk * kLnBlockRows;
-    const long long left = rows - r0;
-    const int nr = (int)(left < kLnBlockRows ? left : kLnBlockRows);
-    const int lr = warp * 2;
-    if (lr < nr) {
-      const bool has1 = lr + 1 < nr;
-      const uint4* src0 = reinterpret_cast<const uint4*>(ln_smem + s * stage_bytes + (size_t)lr * row_bytes);
-      const uint4* src1 = reinterpret_cast<const uint4*>(ln_smem + s * stage_bytes + (size_t)(lr + 1) * row_bytes);
-      uint64_t f0[NV][4], f1[NV][4];
-      uint64_t s0 = 0ull, s1 = 0ull;                 // {0.f, 0.f}
+    const long long row = blk * kLnBlockRows + warp;
+    if (row < rows) {
+      const uint4* src = reinterpret_cast<const uint4*>(ln_smem + s * stage_bytes + (size_t)warp * row_bytes);
+      uint64_t f[NV][4];
+      uint64_t sum = 0ull;                            // {0.f, 0.f}
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int v = lane + 32 * i;
-        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u);
-        if (v < V) {
-          a = src0[v];
-          if (has1) b = src1[v];
-        }
-        f0[i][0] = bf16x2_to_f2(a.x); f0[i][1] = bf16x2_to_f2(a.y); f0[i][2] = bf16x2_to_f2(a.z); f0[i][3] = bf16x2_to_f2(a.w);
-        f1[i][0] = bf16x2_to_f2(b.x); f1[i][1] = bf16x2_to_f2(b.y); f1[i][2] = bf16x2_to_f2(b.z); f1[i][3] = bf16x2_to_f2(b.w);
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        if (v < V) a = src[v];
+        f[i][0] = bf16x2_to_f2(a.x); f[i][1] = bf16x2_to_f2(a.y); f[i][2] = bf16x2_to_f2(a.z); f[i][3] = bf16x2_to_f2(a.w);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { s0 = add_f2(s0, f0[i][j]); s1 = add_f2(s1, f1[i][j]); }
+        for (int j = 0; j < 4; ++j) sum = add_f2(sum, f[i][j]);
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);          // the rows are in registers: hand the slot back before the arithmetic
-      const float m0 = warp_sum(f2_hsum(s0)) * inv_cols, m1 = warp_sum(f2_hsum(s1)) * inv_cols;
-      const uint64_t nm0 = pack_f2(-m0, -m0), nm1 = pack_f2(-m1, -m1);
-      uint64_t q0 = 0ull, q1 = 0ull;
+      if (lane == 0) mbar_arrive(&empty[s]);          // the row is in registers: hand the slot back before the arithmetic
+      const float mean = warp_sum(f2_hsum(sum)) * inv_cols;
+      const uint64_t nm = pack_f2(-mean, -mean);
+      uint64_t q = 0ull;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         if (lane + 32 * i < V) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            f0[i][j] = add_f2(f0[i][j], nm0); q0 = fma_f2(f0[i][j], f0[i][j], q0);
-            f1[i][j] = add_f2(f1[i][j], nm1); q1 = fma_f2(f1[i][j], f1[i][j], q1);
-          }
+          for (int j = 0; j < 4; ++j) { f[i][j] = add_f2(f[i][j], nm); q = fma_f2(f[i][j], f[i][j], q); }
         }
       }
-      const float rs0 = rsqrtf(warp_sum(f2_hsum(q0)) * inv_cols + eps), rs1 = rsqrtf(warp_sum(f2_hsum(q1)) * inv_cols + eps);
-      const uint64_t r0p = pack_f2(rs0, rs0), r1p = pack_f2(rs1, rs1);
-      __nv_bfloat16* o0 = out + (r0 + lr) * cols;
+      const float rs = rsqrtf(warp_sum(f2_hsum(q)) * inv_cols + eps);
+      const uint64_t rp = pack_f2(rs, rs);
+      __nv_bfloat16* o = out + row * cols;
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int v = lane + 32 * i;
@@ -513,21 +501,12 @@ layernorm_bulk_kernel(const __nv_bfloat16* __restrict__ x, const float* __restri
           const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
           const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
           const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-          const uint64_t gg[4] = {pack_f2(g0.x, g0.y), pack_f2(g0.z, g0.w), pack_f2(g1.x, g1.y), pack_f2(g1.z, g1.w)};
-          const uint64_t bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
-          uint4 y0, y1;
-          y0.x = f2_to_bf16x2(fma_f2(f0[i][0], mul_f2(r0p, gg[0]), bb[0]));
-          y0.y = f2_to_bf16x2(fma_f2(f0[i][1], mul_f2(r0p, gg[1]), bb[1]));
-          y0.z = f2_to_bf16x2(fma_f2(f0[i][2], mul_f2(r0p, gg[2]), bb[2]));
-          y0.w = f2_to_bf16x2(fma_f2(f0[i][3], mul_f2(r0p, gg[3]), bb[3]));
-          *reinterpret_cast<uint4*>(o0 + v * 8) = y0;
-          if (has1) {
-            y1.x = f2_to_bf16x2(fma_f2(f1[i][0], mul_f2(r1p, gg[0]), bb[0]));
-            y1.y = f2_to_bf16x2(fma_f2(f1[i][1], mul_f2(r1p, gg[1]), bb[1]));
-            y1.z = f2_to_bf16x2(fma_f2(f1[i][2], mul_f2(r1p, gg[2]), bb[2]));
-            y1.w = f2_to_bf16x2(fma_f2(f1[i][3], mul_f2(r1p, gg[3]), bb[3]));
-            *reinterpret_cast<uint4*>(o0 + cols + v * 8) = y1;
-          }
+          uint4 y;
+          y.x = f2_to_bf16x2(fma_f2(f[i][0], mul_f2(rp, pack_f2(g0.x, g0.y)), pack_f2(b0.x, b0.y)));
+          y.y = f2_to_bf16x2(fma_f2(f[i][1], mul_f2(rp, pack_f2(g0.z, g0.w)), pack_f2(b0.z, b0.w)));
+          y.z = f2_to_bf16x2(fma_f2(f[i][2], mul_f2(rp, pack_f2(g1.x, g1.y)), pack_f2(b1.x, b1.y)));
+          y.w = f2_to_bf16x2(fma_f2(f[i][3], mul_f2(rp, pack_f2(g1.z, g1.w)), pack_f2(b1.z, b1.w)));
+          *reinterpret_cast<uint4*>(o + v * 8) = y;
         }
       }
     } else {
@@ -618,16 +597,14 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
   if (occ < 0) return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
   int G = num_sms() * occ;
   if (G > kGnMaxChunks) G = kGnMaxChunks;
-  const double sample_bytes = (double)hw * ct * 2.0;
-  int nteams = 1;
-  while (nteams * 2 <= batch && nteams * 2 <= 8 && nteams * 2 * 3.0 * sample_bytes <= 48e6 && G / (nteams * 2) >= 8) nteams *= 2;
-  const int team_size = G / nteams;
-  const int depth = (nteams * 3.0 * sample_bytes <= 64e6) ? 2 : 1;
+  int cps = G / batch;                                  // chunks (= CTAs) per sample
+  if (cps < 1) return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
+  if (cps > hw) cps = (int)hw;
   float* partial = work;
   float* table = work + (int64_t)batch * kGnMaxChunks * groups * 2;
-  gn_fused_kernel<<<dim3(team_size * nteams), dim3(threads), smem, stream>>>(
+  gn_fused_kernel<<<dim3(cps * batch), dim3(threads), smem, stream>>>(
       (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
-      (__nv_bfloat16*)out, partial, table, (unsigned*)sync, batch, team_size, nteams, depth);
+      (__nv_bfloat16*)out, partial, table, (unsigned*)sync, batch, cps);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -647,13 +624,13 @@ extern "C" int fd_layernorm(const void* x, const float* gamma, const float* beta
     const size_t smem = (size_t)kLnStages * kLnBlockRows * cols * 2;
     const int nvb = (cols / 8 + 31) / 32;
     const long long nblk = (rows + kLnBlockRows - 1) / kLnBlockRows;
-    long long grid = (long long)num_sms() * (smem <= 100 * 1024 ? 2 : 1);
+    long long grid = (long long)num_sms() * (smem <= 104 * 1024 ? 2 : 1);
     if (grid > nblk) grid = nblk;
 #define FD_LNB(NV)                                                                                                              \
   do {                                                                                                                          \
     static bool attr_set = false;                                                                                               \
     if (!attr_set) {                                                                                                            \
-      FD_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));  \
+      FD_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bulk_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));  \
       attr_set = true;                                                                                                          \
     }                                                                                                                           \
     layernorm_bulk_kernel<NV><<<dim3((unsigned)grid), dim3((kLnWarps + 1) * 32), smem, stream>>>(                               \

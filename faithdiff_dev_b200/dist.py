@@ -49,6 +49,14 @@ def shard_units(num_tiles, rank, world_size):
     return list(range(lo, hi))
 
 
+def shard_images(num_images, rank, world_size):
+    """BASELINE config 5 (a batch of independent images, e.g. 32 x 512 -> 2048): plain data parallelism, no exchange.
+    The reference restores one image per call (`assert b == 1`, pipeline_FaithDiff_tlc.py:171,1220), so the batch is a list of
+    calls; rank r takes the contiguous balanced range [r*N/W, (r+1)*N/W) and runs each through a single-GPU pipeline."""
+    lo, hi = rank * num_images // world_size, (rank + 1) * num_images // world_size
+    return list(range(lo, hi))
+
+
 # measured replay cost (ms) by number of SAMPLES (= units) per launch (9, 11, 13, 15 interpolated)
 UNIT_REPLAY_COST_MS = {1: 15.60, 2: 20.73, 3: 26.28, 4: 35.80, 5: 42.89, 6: 48.70, 7: 56.53, 8: 64.75, 9: 72.3, 10: 79.83,
                        11: 87.7, 12: 95.50, 13: 103.0, 14: 110.47, 15: 118.5, 16: 126.53}

@@ -102,14 +102,15 @@ def _device_tables(in_w, in_h, out_w, out_h, device):
 
 def resize_lanczos(image, size, device="cuda"):
     """`image.resize(size, Image.LANCZOS)` on the GPU, bit-identical to PIL for 8-bit images.
-    image: PIL image (L / RGB / RGBA), or u8 HWC numpy array / torch tensor (host or device); size = (width, height).
+    image: PIL image (L / RGB / CMYK ...; not RGBA: PIL premultiplies alpha), or u8 HWC numpy array / torch tensor (host or device); size = (width, height).
     Returns a u8 HWC tensor on `device` (feed it to the pipeline as `lr_img`, or `Image.fromarray(t.cpu().numpy())`)."""
     import torch
     from . import ops
     if isinstance(image, Image.Image):
-        if image.mode not in ("L", "RGB", "RGBA"):
-            raise ValueError("resize_lanczos: PIL mode %r is not an 8-bit interleaved image" % (image.mode,))
-        image = np.asarray(image)
+        if image.mode not in ("L", "RGB", "CMYK", "YCbCr", "HSV", "LAB"):
+            # RGBA / LA are excluded on purpose: PIL premultiplies alpha around the resample; the path feeds RGB
+            raise ValueError("resize_lanczos: PIL mode %r is not a plain 8-bit interleaved image" % (image.mode,))
+        image = np.array(image)
     t = torch.as_tensor(image)
     if t.dtype != torch.uint8 or t.dim() not in (2, 3):
         raise ValueError("resize_lanczos expects a u8 HW or HWC image, got %s %s" % (t.dtype, tuple(t.shape)))

@@ -71,3 +71,11 @@ def test_shard_and_launch_plan():
     assert sorted(len(x) for x in plan_launch_groups(list(range(28)), [1, 2, 3, 4])) == [4] * 7
     assert sorted(len(x) for x in plan_launch_groups(list(range(28)), range(1, 9))) == [7] * 4
     assert sorted(len(x) for x in plan_launch_groups(list(range(7)), [1, 2, 3, 4])) == [3, 4]
+
+
+def test_shard_images_partitions_the_batch():
+    from faithdiff_dev_b200.dist import shard_images
+    for n, w in [(32, 8), (32, 1), (5, 8), (9, 4), (0, 2)]:
+        parts = [shard_images(n, r, w) for r in range(w)]
+        assert sorted(i for p in parts for i in p) == list(range(n))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1

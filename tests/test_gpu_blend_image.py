@@ -153,13 +153,13 @@ def test_color_fix_golden(fd, golden_dir, mode):
 
 @pytest.mark.parametrize("w,h,ow,oh,mode", [(37, 23, 74, 46, "RGB"), (64, 48, 128, 96, "RGB"), (50, 40, 200, 160, "RGB"),
                                             (100, 80, 50, 40, "RGB"), (33, 17, 40, 17, "RGB"), (31, 29, 31, 60, "RGB"),
-                                            (120, 90, 37, 29, "RGBA"), (16, 16, 129, 67, "L"), (480, 270, 960, 540, "RGB"),
+                                            (120, 90, 37, 29, "CMYK"), (16, 16, 129, 67, "L"), (480, 270, 960, 540, "RGB"),
                                             (1920, 1080, 3840, 2160, "RGB")])
 def test_lanczos_resize_bit_exact_vs_pil(fd, w, h, ow, oh, mode):
     """`image.resize((w*s, h*s), Image.LANCZOS)` of the caller (test_wo_llava.py:81) on the GPU: integer work, bit-exact."""
     from PIL import Image
     from faithdiff_dev_b200.image_process import resize_lanczos
-    ch = {"L": 1, "RGB": 3, "RGBA": 4}[mode]
+    ch = {"L": 1, "RGB": 3, "CMYK": 4}[mode]
     a = np.random.default_rng(w + 7 * oh).integers(0, 256, size=(h, w, ch) if ch > 1 else (h, w), dtype=np.uint8)
     img = Image.fromarray(a, mode)
     ref = np.asarray(img.resize((ow, oh), Image.LANCZOS))
@@ -168,3 +168,5 @@ def test_lanczos_resize_bit_exact_vs_pil(fd, w, h, ow, oh, mode):
     assert np.array_equal(got.cpu().numpy(), ref)
     # tensor inputs (host and device) take the same path
     assert torch.equal(resize_lanczos(torch.from_numpy(a).cuda(), (ow, oh)), got)
+    with pytest.raises(ValueError):                  # PIL premultiplies alpha for RGBA: not this kernel's contract
+        resize_lanczos(Image.new("RGBA", (8, 8)), (16, 16))
