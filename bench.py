@@ -399,7 +399,7 @@ def main():
                         "how": "same instrumented pass: algorithmic bytes (bf16 read + write, 4 B/element) of every GroupNorm / LayerNorm "
                                "call of the UNet evaluation / summed CUDA-event durations (one launch per call)",
                         "kernels": {}}
-            for name, kern in (("groupnorm", "gn_fused_kernel"), ("layernorm", "layernorm_bulk_kernel")):
+            for name, kern in (("groupnorm", "gn_fused_kernel"), ("layernorm", "layernorm_kernel")):
                 h = r["hbm"].get(name)
                 if h:
                     a = h["bytes"] / h["seconds"] / 1e9

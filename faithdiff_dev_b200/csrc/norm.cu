@@ -5,6 +5,7 @@
 //   UNet's tensors (<= 42 MB vs 126 MB L2), so DRAM traffic is ~ one read + one write.
 //   Two NHWC sources are treated as one channel-concatenated tensor (the up-block torch.cat never materialises).
 //   LayerNorm: one warp per row, row held in registers, warp-shuffle reductions.
+#include <type_traits>
 #include "common.cuh"
 #include "../../include/faithdiff_b200.h"
 
@@ -159,28 +160,37 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void acc8(const uint4& u, float (&s)[8], float (&q)[8]) {
-  float2 t;
-  t = unpack_bf16(u.x); s[0] += t.x; q[0] = fmaf(t.x, t.x, q[0]); s[1] += t.y; q[1] = fmaf(t.y, t.y, q[1]);
-  t = unpack_bf16(u.y); s[2] += t.x; q[2] = fmaf(t.x, t.x, q[2]); s[3] += t.y; q[3] = fmaf(t.y, t.y, q[3]);
-  t = unpack_bf16(u.z); s[4] += t.x; q[4] = fmaf(t.x, t.x, q[4]); s[5] += t.y; q[5] = fmaf(t.y, t.y, q[5]);
-  t = unpack_bf16(u.w); s[6] += t.x; q[6] = fmaf(t.x, t.x, q[6]); s[7] += t.y; q[7] = fmaf(t.y, t.y, q[7]);
+// packed fp32x2 helpers (the kernel is otherwise bound by instruction issue, not by HBM: the scalar version with an IEEE
+// division in SiLU needed ~20 lane-instructions per element against the ~22 per element an SM can issue at HBM speed)
+__device__ __forceinline__ uint64_t bf2_f2(uint32_t u) { return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ void acc8(const uint4& u, uint64_t (&s)[4], uint64_t (&q)[4]) {
+  const uint64_t f0 = bf2_f2(u.x), f1 = bf2_f2(u.y), f2 = bf2_f2(u.z), f3 = bf2_f2(u.w);
+  s[0] = add_f2(s[0], f0); q[0] = fma_f2(f0, f0, q[0]);
+  s[1] = add_f2(s[1], f1); q[1] = fma_f2(f1, f1, q[1]);
+  s[2] = add_f2(s[2], f2); q[2] = fma_f2(f2, f2, q[2]);
+  s[3] = add_f2(s[3], f3); q[3] = fma_f2(f3, f3, q[3]);
 }
-__device__ __forceinline__ uint4 norm8(const uint4& u, const float (&a)[8], const float (&b)[8], int silu) {
-  float f[8];
-  float2 t;
-  t = unpack_bf16(u.x); f[0] = t.x; f[1] = t.y;
-  t = unpack_bf16(u.y); f[2] = t.x; f[3] = t.y;
-  t = unpack_bf16(u.z); f[4] = t.x; f[5] = t.y;
-  t = unpack_bf16(u.w); f[6] = t.x; f[7] = t.y;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], a[j], b[j]);
-  if (silu) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = silu_f(f[j]);
+// y = x*a + b, then SiLU as y * rcp(1 + exp2(-y*log2e)) (approximate MUFU reciprocal instead of an IEEE division)
+template <bool kSilu>
+__device__ __forceinline__ uint32_t norm2(uint32_t u, uint64_t a, uint64_t b) {
+  const uint64_t y = fma_f2(bf2_f2(u), a, b);
+  float y0, y1;
+  unpack_f2(y, y0, y1);
+  if (kSilu) {
+    float e0, e1;
+    unpack_f2(mul_f2(y, pack_f2(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
+    float d0, d1;
+    unpack_f2(add_f2(pack_f2(fast_exp2(e0), fast_exp2(e1)), pack_f2(1.f, 1.f)), d0, d1);
+    y0 = __fdividef(y0, d0);
+    y1 = __fdividef(y1, d1);
   }
+  return pack_bf16(y0, y1);
+}
+template <bool kSilu>
+__device__ __forceinline__ uint4 norm8(const uint4& u, const uint64_t (&a)[4], const uint64_t (&b)[4]) {
   uint4 o;
-  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  o.x = norm2<kSilu>(u.x, a[0], b[0]); o.y = norm2<kSilu>(u.y, a[1], b[1]);
+  o.z = norm2<kSilu>(u.z, a[2], b[2]); o.w = norm2<kSilu>(u.w, a[3], b[3]);
   return o;
 }
 
@@ -214,9 +224,9 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
 
   // ---- (1) statistics of the chunk
   {
-    float s[8], q[8];
+    uint64_t s[4], q[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { s[j] = 0ull; q[j] = 0ull; }
     const __nv_bfloat16* ptr = src + (p0 + r) * pitch;
     long long k = 0;
     for (; k + 4 <= n; k += 4) {
@@ -232,7 +242,10 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
       float* ss = sm + (size_t)r * ct + ch;
       float* sq = sm + (size_t)(R + r) * ct + ch;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ss[j] = s[j]; sq[j] = q[j]; }
+      for (int j = 0; j < 4; ++j) {
+        unpack_f2(s[j], ss[2 * j], ss[2 * j + 1]);
+        unpack_f2(q[j], sq[2 * j], sq[2 * j + 1]);
+      }
     }
   }
   __syncthreads();
@@ -310,30 +323,47 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     const float* tb = table + (long long)b * 2 * ct + ch;
     const float4 a0 = __ldcg(reinterpret_cast<const float4*>(tb)), a1 = __ldcg(reinterpret_cast<const float4*>(tb + 4));
     const float4 b0 = __ldcg(reinterpret_cast<const float4*>(tb + ct)), b1 = __ldcg(reinterpret_cast<const float4*>(tb + ct + 4));
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float sft[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const uint64_t a[4] = {pack_f2(a0.x, a0.y), pack_f2(a0.z, a0.w), pack_f2(a1.x, a1.y), pack_f2(a1.z, a1.w)};
+    const uint64_t sft[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
     const long long ostride = (long long)R * ct;
     const __nv_bfloat16* ptr = src + (p0 + r + (n - 1) * R) * pitch;
     __nv_bfloat16* dst = out + ((long long)b * hw + p0 + r + (n - 1) * R) * ct + ch;
-    long long k = 0;
-    for (; k + 4 <= n; k += 4) {
-      const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(ptr));
-      const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(ptr - stride));
-      const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(ptr - 2 * stride));
-      const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(ptr - 3 * stride));
-      *reinterpret_cast<uint4*>(dst) = norm8(u0, a, sft, silu);
-      *reinterpret_cast<uint4*>(dst - ostride) = norm8(u1, a, sft, silu);
-      *reinterpret_cast<uint4*>(dst - 2 * ostride) = norm8(u2, a, sft, silu);
-      *reinterpret_cast<uint4*>(dst - 3 * ostride) = norm8(u3, a, sft, silu);
-      ptr -= 4 * stride;
-      dst -= 4 * ostride;
-    }
-    for (; k < n; ++k, ptr -= stride, dst -= ostride) *reinterpret_cast<uint4*>(dst) = norm8(__ldcs(reinterpret_cast<const uint4*>(ptr)), a, sft, silu);
+    auto run = [&](auto silu_tag) {
+      constexpr bool kSilu = decltype(silu_tag)::value;
+      long long k = 0;
+      for (; k + 4 <= n; k += 4) {
+        const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(ptr));
+        const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(ptr - stride));
+        const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(ptr - 2 * stride));
+        const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(ptr - 3 * stride));
+        *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(u0, a, sft);
+        *reinterpret_cast<uint4*>(dst - ostride) = norm8<kSilu>(u1, a, sft);
+        *reinterpret_cast<uint4*>(dst - 2 * ostride) = norm8<kSilu>(u2, a, sft);
+        *reinterpret_cast<uint4*>(dst - 3 * ostride) = norm8<kSilu>(u3, a, sft);
+        ptr -= 4 * stride;
+        dst -= 4 * ostride;
+      }
+      for (; k < n; ++k, ptr -= stride, dst -= ostride)
+        *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(__ldcs(reinterpret_cast<const uint4*>(ptr)), a, sft);
+    };
+    if (silu) run(std::true_type{}); else run(std::false_type{});
   }
 }
 
 // one warp per PAIR of rows (both rows' loads are issued before either reduction: twice the bytes in flight per warp);
-// cols <= 1280 (5 vectors of 8 per lane); single-pass sum / sum-of-squares in fp32 with a mean-shifted second moment
+// cols <= 1280 (5 vectors of 8 per lane); sum, then a mean-shifted second moment, in packed fp32x2 arithmetic: 4 instead of
+// 7.5 lane-instructions per element (at HBM speed an SM has to retire ~11 elements per clock out of 128 issue slots)
+__device__ __forceinline__ uint64_t ln_bf2_f2(uint32_t u) { return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ float ln_hsum(uint64_t v) {
+  float lo, hi;
+  unpack_f2(v, lo, hi);
+  return lo + hi;
+}
+__device__ __forceinline__ uint32_t ln_out2(uint64_t d, uint64_t rs, uint64_t g, uint64_t b) {
+  float lo, hi;
+  unpack_f2(fma_f2(d, mul_f2(rs, g), b), lo, hi);
+  return pack_bf16(lo, hi);
+}
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
@@ -346,41 +376,48 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   if (row0 >= rows) return;
   const bool has1 = row0 + 1 < rows;
   const int V = cols >> 3;
-  float f[2][NV][8];
+  const float inv_cols = 1.f / (float)cols;
+  uint64_t f0[NV][4], f1[NV][4];
+  uint4 u0[NV], u1[NV];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int v = lane + 32 * i;
-      if (v < V && (r == 0 || has1)) load8(x + (row0 + r) * cols + v * 8, f[r][i]);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[r][i][j] = 0.f;
-      }
+  for (int i = 0; i < NV; ++i) {                       // all loads of both rows first
+    const int v = lane + 32 * i;
+    u0[i] = make_uint4(0u, 0u, 0u, 0u);
+    u1[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (v < V) {
+      u0[i] = __ldg(reinterpret_cast<const uint4*>(x + row0 * cols + v * 8));
+      if (has1) u1[i] = __ldg(reinterpret_cast<const uint4*>(x + (row0 + 1) * cols + v * 8));
     }
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s0 += f[0][i][j]; s1 += f[1][i][j]; }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
-  const float m0 = s0 / cols, m1 = s1 / cols;
-  float q0 = 0.f, q1 = 0.f;
+  }
+  uint64_t s0 = 0ull, s1 = 0ull;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    const int v = lane + 32 * i;
-    if (v < V) {
+    f0[i][0] = ln_bf2_f2(u0[i].x); f0[i][1] = ln_bf2_f2(u0[i].y); f0[i][2] = ln_bf2_f2(u0[i].z); f0[i][3] = ln_bf2_f2(u0[i].w);
+    f1[i][0] = ln_bf2_f2(u1[i].x); f1[i][1] = ln_bf2_f2(u1[i].y); f1[i][2] = ln_bf2_f2(u1[i].z); f1[i][3] = ln_bf2_f2(u1[i].w);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float d0 = f[0][i][j] - m0, d1 = f[1][i][j] - m1;
-        q0 += d0 * d0; q1 += d1 * d1;
+    for (int j = 0; j < 4; ++j) { s0 = add_f2(s0, f0[i][j]); s1 = add_f2(s1, f1[i][j]); }
+  }
+  float m0 = ln_hsum(s0), m1 = ln_hsum(s1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { m0 += __shfl_xor_sync(0xffffffffu, m0, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o); }
+  m0 *= inv_cols; m1 *= inv_cols;
+  const uint64_t nm0 = pack_f2(-m0, -m0), nm1 = pack_f2(-m1, -m1);
+  uint64_t q0 = 0ull, q1 = 0ull;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    if (lane + 32 * i < V) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f0[i][j] = add_f2(f0[i][j], nm0); q0 = fma_f2(f0[i][j], f0[i][j], q0);
+        f1[i][j] = add_f2(f1[i][j], nm1); q1 = fma_f2(f1[i][j], f1[i][j], q1);
       }
     }
   }
+  float v0 = ln_hsum(q0), v1 = ln_hsum(q1);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
-  const float rs0 = rsqrtf(q0 / cols + eps), rs1 = rsqrtf(q1 / cols + eps);
+  for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
+  const float rs0 = rsqrtf(v0 * inv_cols + eps), rs1 = rsqrtf(v1 * inv_cols + eps);
+  const uint64_t r0p = pack_f2(rs0, rs0), r1p = pack_f2(rs1, rs1);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
@@ -389,19 +426,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      float o0[8], o1[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        o0[j] = (f[0][i][j] - m0) * rs0 * gg[j] + bb[j];
-        o1[j] = (f[1][i][j] - m1) * rs1 * gg[j] + bb[j];
+      const uint64_t gg[4] = {pack_f2(g0.x, g0.y), pack_f2(g0.z, g0.w), pack_f2(g1.x, g1.y), pack_f2(g1.z, g1.w)};
+      const uint64_t bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
+      uint4 y;
+      y.x = ln_out2(f0[i][0], r0p, gg[0], bb[0]); y.y = ln_out2(f0[i][1], r0p, gg[1], bb[1]);
+      y.z = ln_out2(f0[i][2], r0p, gg[2], bb[2]); y.w = ln_out2(f0[i][3], r0p, gg[3], bb[3]);
+      *reinterpret_cast<uint4*>(out + row0 * cols + v * 8) = y;
+      if (has1) {
+        y.x = ln_out2(f1[i][0], r1p, gg[0], bb[0]); y.y = ln_out2(f1[i][1], r1p, gg[1], bb[1]);
+        y.z = ln_out2(f1[i][2], r1p, gg[2], bb[2]); y.w = ln_out2(f1[i][3], r1p, gg[3], bb[3]);
+        *reinterpret_cast<uint4*>(out + (row0 + 1) * cols + v * 8) = y;
       }
-      store8(out + row0 * cols + v * 8, o0);
-      if (has1) store8(out + (row0 + 1) * cols + v * 8, o1);
     }
   }
 }
+
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm, persistent + bulk-copy pipelined.  A producer thread streams blocks of 16 contiguous rows into a 5-stage
 // shared-memory ring with ONE cp.async.bulk each (the rows of a block are contiguous in memory) completing on an mbarrier;
@@ -617,8 +656,8 @@ extern "C" int fd_layernorm(const void* x, const float* gamma, const float* beta
   FD_REQUIRE(cols % 8 == 0 && cols <= 1280, "fd_layernorm: cols %d unsupported (need %%8==0 and <= 1280)", cols);
   static int bulk = -1;
   if (bulk < 0) {
-    const char* e = getenv("FD_LN_BULK");
-    bulk = (e && e[0] == '0') ? 0 : 1;
+    const char* e = getenv("FD_LN_BULK");        // opt-in experiment: measured slower than layernorm_kernel
+    bulk = (e && e[0] == '1') ? 1 : 0;
   }
   if (bulk && rows >= 1024 && ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0)) {
     const size_t smem = (size_t)kLnStages * kLnBlockRows * cols * 2;
