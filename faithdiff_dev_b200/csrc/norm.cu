@@ -142,12 +142,13 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 // Fused GroupNorm(+SiLU): ONE launch instead of partial / finalize / apply.
 //   The grid is the GPU's co-resident CTA slots (occupancy x SMs).  Each CTA owns ONE pixel chunk of ONE sample:
 //   (1) it reduces the chunk to per-group partial sums (the deterministic scheme of gn_partial_kernel, four 16-byte loads in
-//   flight per thread) and arrives on the sample's counter; (2) the LAST arriver of a sample combines the partials in fp64 in
-//   chunk order (deterministic whoever it is), writes the per-channel scale/shift table and releases the sample's ready flag;
-//   (3) every CTA acquires its sample's flag and streams y = silu(x*scale + shift) over its own chunk BACKWARDS, so the pixels
-//   it read last — the ones most likely still in L2 — are re-read first.  All loads of the statistics pass are issued before
-//   the first store of the apply pass: the fence before the arrive never has a store stream to wait for (a first version that
-//   interleaved per-sample statistics with the apply stores of the previous sample spent its time in those fences).
+//   flight per thread, packed fp32x2 accumulation), publishes them and arrives on the sample's counter; (2) it waits until all
+//   chunks of ITS sample have arrived (one acquire poll; other samples are not waited for), then combines the sample's partials
+//   itself in fp64 in chunk order — every CTA of a sample gets identical bits, and no finalizer CTA / table round trip sits on
+//   the critical path; (3) it streams y = silu(x*scale + shift) over its own chunk BACKWARDS, so the pixels it read last — the
+//   ones most likely still in L2 — are re-read first.  All loads of the statistics pass are issued before the first store of
+//   the apply pass: the fence before the arrive never has a store stream to wait for (a first version that interleaved
+//   per-sample statistics with the apply stores of the previous sample spent its time in those fences: 0.14 of HBM peak).
 //   Counters reset themselves (the last CTA past the wait clears them), so CUDA-graph replays need no memset node.
 //   Requires all CTAs co-resident: plain stream-ordered launch (never PDL), grid sized by the occupancy API.
 constexpr int kGnSyncMaxBatch = 64;
@@ -170,19 +171,22 @@ __device__ __forceinline__ void acc8(const uint4& u, uint64_t (&s)[4], uint64_t 
   s[2] = add_f2(s[2], f2); q[2] = fma_f2(f2, f2, q[2]);
   s[3] = add_f2(s[3], f3); q[3] = fma_f2(f3, f3, q[3]);
 }
-// y = x*a + b, then SiLU as y * rcp(1 + exp2(-y*log2e)) (approximate MUFU reciprocal instead of an IEEE division)
+// kSilu: the table holds a/2 and b/2, so h = x*(a/2) + b/2 = y/2 and silu(y) = y*sigmoid(y) = h + h*tanh(h): ONE MUFU op per
+// element (tanh.approx, relative error 2^-11, i.e. a quarter of a bf16 rounding step) instead of exp2 + reciprocal — at 2 MUFU
+// ops per element the 16-lane MUFU pipe alone needed 32 us of the 14 x 128^2 x 320 tensor's 60 us HBM budget.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 template <bool kSilu>
 __device__ __forceinline__ uint32_t norm2(uint32_t u, uint64_t a, uint64_t b) {
-  const uint64_t y = fma_f2(bf2_f2(u), a, b);
+  uint64_t y = fma_f2(bf2_f2(u), a, b);
   float y0, y1;
   unpack_f2(y, y0, y1);
   if (kSilu) {
-    float e0, e1;
-    unpack_f2(mul_f2(y, pack_f2(-1.4426950408889634f, -1.4426950408889634f)), e0, e1);
-    float d0, d1;
-    unpack_f2(add_f2(pack_f2(fast_exp2(e0), fast_exp2(e1)), pack_f2(1.f, 1.f)), d0, d1);
-    y0 = __fdividef(y0, d0);
-    y1 = __fdividef(y1, d1);
+    y = fma_f2(y, pack_f2(tanh_approx(y0), tanh_approx(y1)), y);
+    unpack_f2(y, y0, y1);
   }
   return pack_bf16(y0, y1);
 }
@@ -197,11 +201,9 @@ __device__ __forceinline__ uint4 norm8(const uint4& u, const uint64_t (&a)[4], c
 __global__ void __launch_bounds__(512, 2)
 gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, long long hw,
                 int groups, int R, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ partial, float* __restrict__ table,
-                unsigned* __restrict__ sync, int batch, int cps) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ partial, unsigned* __restrict__ sync, int batch, int cps) {
   extern __shared__ float sm[];
   __shared__ float s_mean[64], s_rstd[64];
-  __shared__ int s_last;
   const int b = blockIdx.x / cps, m = blockIdx.x - b * cps;     // sample, chunk of the sample
   if (b >= batch) return;
   const int tid = threadIdx.x;
@@ -215,7 +217,6 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
   const long long p0 = ((long long)m * per < hw) ? (long long)m * per : hw;
   const long long p1 = (p0 + per < hw) ? p0 + per : hw;
   unsigned* arrive = sync + b;
-  unsigned* ready = sync + kGnSyncMaxBatch + b;
   unsigned* done = sync + 2 * kGnSyncMaxBatch + b;
   const __nv_bfloat16* src = from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0);
   // pixels of this thread: p0 + r + k*R, k in [0, n)
@@ -266,12 +267,21 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     __threadfence();
   }
   __syncthreads();
-  if (tid == 0) s_last = (atomicAdd(arrive, 1u) == (unsigned)(cps - 1));
+  // ---- (2) arrive on the sample's counter and wait until all its chunks have: one flag round trip, then EVERY CTA of the sample
+  // combines the partials itself (fp64, chunk order: identical bits in every CTA) - cheaper than a finalizer CTA publishing a table
+  if (tid == 0) {
+    atomicAdd(arrive, 1u);
+    const long long t0 = clock64();
+    while (ld_acquire_u32(arrive) < (unsigned)cps) {
+      __nanosleep(32);
+      if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a CTA of the sample never arrived (not co-resident?) - fail, do not hang
+    }
+    if (atomicAdd(done, 1u) == (unsigned)(cps - 1)) {   // every CTA of the sample is past the wait: recycle its counters
+      *arrive = 0u; *done = 0u;
+    }
+  }
   __syncthreads();
-
-  // ---- (2) the last arriver of the sample finalises it
-  if (s_last) {                                      // CTA-uniform
-    __threadfence();
+  {
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
     for (int g = warp; g < groups; g += nwarps) {
       double s = 0.0, q = 0.0;
@@ -294,35 +304,22 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
         s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
       }
     }
-    __syncthreads();
-    float* tb = table + (long long)b * 2 * ct;
-    for (int c = tid; c < ct; c += blockDim.x) {
-      const int g = c / cpg;
-      const float sc = s_rstd[g] * gamma[c];
-      tb[c] = sc;
-      tb[ct + c] = beta[c] - s_mean[g] * sc;
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) st_release_u32(ready, 1u);
-  }
-
-  // ---- (3) wait for the sample's table, then normalise the chunk back to front
-  if (tid == 0) {
-    const long long t0 = clock64();
-    while (ld_acquire_u32(ready) == 0u) {
-      __nanosleep(32);
-      if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s: a CTA of the sample never arrived (not co-resident?) - fail, do not hang
-    }
-    if (atomicAdd(done, 1u) == (unsigned)(cps - 1)) {   // every CTA of the sample is past the wait: recycle its counters
-      *arrive = 0u; *ready = 0u; *done = 0u;
-    }
   }
   __syncthreads();
+
+  // ---- (3) normalise the chunk back to front
   if (n > 0) {
-    const float* tb = table + (long long)b * 2 * ct + ch;
-    const float4 a0 = __ldcg(reinterpret_cast<const float4*>(tb)), a1 = __ldcg(reinterpret_cast<const float4*>(tb + 4));
-    const float4 b0 = __ldcg(reinterpret_cast<const float4*>(tb + ct)), b1 = __ldcg(reinterpret_cast<const float4*>(tb + ct + 4));
+    float sc[8], sh[8];
+    const float half = silu ? 0.5f : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch + j, g = c / cpg;
+      const float t = s_rstd[g] * __ldg(gamma + c);
+      sc[j] = t * half;
+      sh[j] = (__ldg(beta + c) - s_mean[g] * t) * half;
+    }
+    const float4 a0 = make_float4(sc[0], sc[1], sc[2], sc[3]), a1 = make_float4(sc[4], sc[5], sc[6], sc[7]);
+    const float4 b0 = make_float4(sh[0], sh[1], sh[2], sh[3]), b1 = make_float4(sh[4], sh[5], sh[6], sh[7]);
     const uint64_t a[4] = {pack_f2(a0.x, a0.y), pack_f2(a0.z, a0.w), pack_f2(a1.x, a1.y), pack_f2(a1.z, a1.w)};
     const uint64_t sft[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
     const long long ostride = (long long)R * ct;
@@ -365,7 +362,7 @@ __device__ __forceinline__ uint32_t ln_out2(uint64_t d, uint64_t rs, uint64_t g,
   return pack_bf16(lo, hi);
 }
 template <int NV>
-__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         long long rows, int cols, float eps) {
   pdl_launch_dependents();
@@ -378,22 +375,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __r
   const int V = cols >> 3;
   const float inv_cols = 1.f / (float)cols;
   uint64_t f0[NV][4], f1[NV][4];
-  uint4 u0[NV], u1[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {                       // all loads of both rows first
-    const int v = lane + 32 * i;
-    u0[i] = make_uint4(0u, 0u, 0u, 0u);
-    u1[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (v < V) {
-      u0[i] = __ldg(reinterpret_cast<const uint4*>(x + row0 * cols + v * 8));
-      if (has1) u1[i] = __ldg(reinterpret_cast<const uint4*>(x + (row0 + 1) * cols + v * 8));
-    }
-  }
   uint64_t s0 = 0ull, s1 = 0ull;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    f0[i][0] = ln_bf2_f2(u0[i].x); f0[i][1] = ln_bf2_f2(u0[i].y); f0[i][2] = ln_bf2_f2(u0[i].z); f0[i][3] = ln_bf2_f2(u0[i].w);
-    f1[i][0] = ln_bf2_f2(u1[i].x); f1[i][1] = ln_bf2_f2(u1[i].y); f1[i][2] = ln_bf2_f2(u1[i].z); f1[i][3] = ln_bf2_f2(u1[i].w);
+    const int v = lane + 32 * i;
+    uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = make_uint4(0u, 0u, 0u, 0u);
+    if (v < V) {
+      u0 = __ldg(reinterpret_cast<const uint4*>(x + row0 * cols + v * 8));
+      if (has1) u1 = __ldg(reinterpret_cast<const uint4*>(x + (row0 + 1) * cols + v * 8));
+    }
+    f0[i][0] = ln_bf2_f2(u0.x); f0[i][1] = ln_bf2_f2(u0.y); f0[i][2] = ln_bf2_f2(u0.z); f0[i][3] = ln_bf2_f2(u0.w);
+    f1[i][0] = ln_bf2_f2(u1.x); f1[i][1] = ln_bf2_f2(u1.y); f1[i][2] = ln_bf2_f2(u1.z); f1[i][3] = ln_bf2_f2(u1.w);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s0 = add_f2(s0, f0[i][j]); s1 = add_f2(s1, f1[i][j]); }
   }
@@ -640,10 +632,9 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
   if (cps < 1) return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
   if (cps > hw) cps = (int)hw;
   float* partial = work;
-  float* table = work + (int64_t)batch * kGnMaxChunks * groups * 2;
   gn_fused_kernel<<<dim3(cps * batch), dim3(threads), smem, stream>>>(
       (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
-      (__nv_bfloat16*)out, partial, table, (unsigned*)sync, batch, cps);
+      (__nv_bfloat16*)out, partial, (unsigned*)sync, batch, cps);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -154,9 +154,17 @@ def test_groupnorm_one_launch_matches_three_launch(ops, B, HW, C0, C1, silu):
     if silu:
         ref = F.silu(ref)
     assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+    # same statistics (fp64 combine); the one-launch kernel evaluates SiLU through tanh.approx (relative error 2^-11 of
+    # sigmoid, absolute error <= |y|/2 * 2^-11), the three-launch kernels through exp + IEEE division
     d = (out.float() - old.float()).abs()
-    assert (d <= 0.0157 * old.float().abs() + 1e-5).all(), d.max().item()       # a few bf16 ulps at most (fp32 sum order)
-    assert (d == 0).float().mean() > 0.98
+    if silu:
+        pre = F.group_norm(xin, 32, g, b, 1e-5).permute(0, 2, 3, 1)
+        bound = 0.0157 * old.float().abs() + 6e-4 * pre.abs() + 1e-5
+    else:
+        bound = 0.0157 * old.float().abs() + 1e-5
+        assert (d == 0).float().mean() > 0.98
+    assert (d <= bound).all(), (d - bound).max().item()
+    assert rel(out, old) < 2e-3
     # counters recycle: repeated eager calls and CUDA-graph replays give the same bits
     for _ in range(3):
         assert torch.equal(ops.groupnorm(x, g, b, 32, 1e-5, silu, x2=x2), out)
