@@ -10,4 +10,5 @@ from .vae import AutoencoderKL, Encoder  # noqa: F401
 from .text_encoder import CLIPTextEncoder, CLIP_L_CONFIG, OPENCLIP_BIGG_CONFIG  # noqa: F401
 from .color_fix import adain_color_fix, wavelet_color_fix  # noqa: F401
 from .create_model import FaithDiff_pipeline, quantize_8bit_state_dict  # noqa: F401
-from .image_process import check_image_size  # noqa: F401
+from .image_process import check_image_size, resize_lanczos  # noqa: F401
+from .bsrnet import RRDBNet, create_bsrnet  # noqa: F401

@@ -48,6 +48,7 @@ _SIGS = {
     "fd_groupnorm_sync_bytes": [],
     "fd_groupnorm_nhwc_fused": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp, vp],
     "fd_layernorm": [vp, vp, vp, vp, i64, i32, f32, vp],
+    "fd_axpby_bf16": [vp, i64, vp, i64, vp, i64, i64, i32, f32, f32, vp],
     "fd_upsample_nearest_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "fd_nchw_to_nhwc": [vp, i32, vp, i32, i32, i64, vp],
     "fd_nhwc_to_nchw": [vp, vp, i32, i32, i32, i64, vp],

@@ -12,6 +12,7 @@ from .pipeline import FaithDiffStableDiffusionXLPipeline
 from .scheduler import DDPMScheduler, EulerDiscreteScheduler
 from .text_encoder import CLIPTextEncoder
 from .unet import UNet2DConditionModel
+from .bsrnet import create_bsrnet  # noqa: F401  (create_FaithDiff_model.py:39-42)
 from .vae import AutoencoderKL
 
 

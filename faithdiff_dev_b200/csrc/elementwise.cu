@@ -54,6 +54,25 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, TO* __r
   }
 }
 
+// ------------------------------------------------------------------ out = alpha*a + beta*b on strided bf16 row views
+__global__ void axpby_kernel(const __nv_bfloat16* __restrict__ a, long long lda, const __nv_bfloat16* __restrict__ b, long long ldb,
+                             __nv_bfloat16* __restrict__ out, long long ldo, int v, long long total, float alpha, float beta) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / v;
+    const int c = (int)(i - r * v) * 8;
+    const uint4 ua = __ldg(reinterpret_cast<const uint4*>(a + r * lda + c));
+    const uint4 ub = __ldg(reinterpret_cast<const uint4*>(b + r * ldb + c));
+    const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_bf16(wa[j]), fb = unpack_bf16(wb[j]);
+      o[j] = pack_bf16(fmaf(alpha, fa.x, beta * fb.x), fmaf(alpha, fa.y, beta * fb.y));
+    }
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------ nearest 2x upsample, NHWC, 16-byte vectors
 __global__ void upsample_nearest_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int h, int w, int oh, int ow,
                                         int v, long long total) {
@@ -420,6 +439,20 @@ extern "C" int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch,
   FD_REQUIRE(x && out && c % 8 == 0, "fd_upsample_nearest_nhwc: channels must be a multiple of 8");
   const long long total = (long long)batch * oh * ow * (c / 8);
   upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>((const uint4*)x, (uint4*)out, h, w, oh, ow, c / 8, total);
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_axpby_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows,
+                             int32_t cols, float alpha, float beta, void* stream_) {
+  FD_REQUIRE(a && b && out && rows >= 0 && cols > 0, "fd_axpby_bf16: bad arguments");
+  FD_REQUIRE(cols % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0 && ldo % 8 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 &&
+                 ((uintptr_t)out % 16) == 0, "fd_axpby_bf16: cols / pitches must be multiples of 8 and pointers 16-byte aligned");
+  if (rows == 0) return 0;
+  const long long total = rows * (cols / 8);
+  axpby_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)a, lda, (const __nv_bfloat16*)b, ldb,
+                                                                       (__nv_bfloat16*)out, ldo, cols / 8, total, alpha, beta);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

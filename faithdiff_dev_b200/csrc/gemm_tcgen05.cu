@@ -361,6 +361,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         } else if (act == 4) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = gelu_erf_f(x[j]);
+        } else if (act == 5) {                       // LeakyReLU(0.2): BSRNet dense blocks / upsampling convs
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.2f * x[j]);
         }
       };
       // GEGLU: the chunk's columns are interleaved (h, g) pairs -> 16 outputs h * gelu(g)
@@ -594,6 +597,7 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FD_REQUIRE(d && d->a[0] && d->b && d->out, "fd_gemm: null operand");
   FD_REQUIRE(d->mode >= 0 && d->mode <= 2, "fd_gemm: bad mode %d", d->mode);
+  FD_REQUIRE(d->act >= 0 && d->act <= 5, "fd_gemm: bad act %d", d->act);
   GemmKParams p;
   memset(&p, 0, sizeof(p));
   const int nsrc = d->a[1] ? 2 : 1;

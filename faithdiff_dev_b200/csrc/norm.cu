@@ -152,6 +152,7 @@ __global__ void gn_apply_kernel(const __nv_bfloat16* __restrict__ x0, int c0, co
 //   Counters reset themselves (the last CTA past the wait clears them), so CUDA-graph replays need no memset node.
 //   Requires all CTAs co-resident: plain stream-ordered launch (never PDL), grid sized by the occupancy API.
 constexpr int kGnSyncMaxBatch = 64;
+constexpr int kGnFusedThreads = 320;     // two CTAs per SM at <= 96 registers: 8 (statistics) / 4+4 (apply) 16-byte loads in flight per thread
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -190,6 +191,21 @@ __device__ __forceinline__ uint32_t norm2(uint32_t u, uint64_t a, uint64_t b) {
   }
   return pack_bf16(y0, y1);
 }
+// 16-byte read-only load with an L2 eviction-priority policy (createpolicy): the statistics pass marks the part of a chunk
+// that fits the L2 budget evict_last so that the apply pass, which walks the chunk backwards, finds it there; everything the
+// apply pass reads is dead afterwards (evict_first), which leaves the room to the output the next kernel consumes.
+__device__ __forceinline__ uint64_t l2_policy(int kind) {       // 0 normal, 1 evict_last, 2 evict_first
+  uint64_t p;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint4 ld16_hint(const void* ptr, uint64_t pol) {
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr), "l"(pol));
+  return v;
+}
 template <bool kSilu>
 __device__ __forceinline__ uint4 norm8(const uint4& u, const uint64_t (&a)[4], const uint64_t (&b)[4]) {
   uint4 o;
@@ -198,10 +214,10 @@ __device__ __forceinline__ uint4 norm8(const uint4& u, const uint64_t (&a)[4], c
   return o;
 }
 
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(kGnFusedThreads, 2)
 gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, long long hw,
                 int groups, int R, float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                __nv_bfloat16* __restrict__ out, float* __restrict__ partial, unsigned* __restrict__ sync, int batch, int cps) {
+                __nv_bfloat16* __restrict__ out, float* __restrict__ partial, unsigned* __restrict__ sync, int batch, int cps, float keep_frac) {
   extern __shared__ float sm[];
   __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.x / cps, m = blockIdx.x - b * cps;     // sample, chunk of the sample
@@ -228,17 +244,21 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     uint64_t s[4], q[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { s[j] = 0ull; q[j] = 0ull; }
+    // keep_frac < 0: no hints; else the LAST keep_frac of the chunk (re-read first by the backwards apply pass) is evict_last
+    const uint64_t pol_keep = l2_policy(keep_frac < 0.f ? 0 : 1), pol_drop = l2_policy(keep_frac < 0.f ? 0 : 2);
+    const long long k_keep = keep_frac < 0.f ? 0 : (long long)((1.f - keep_frac) * (float)n);
     const __nv_bfloat16* ptr = src + (p0 + r) * pitch;
     long long k = 0;
-    for (; k + 4 <= n; k += 4) {
-      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(ptr));
-      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(ptr + stride));
-      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(ptr + 2 * stride));
-      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(ptr + 3 * stride));
-      ptr += 4 * stride;
-      acc8(u0, s, q); acc8(u1, s, q); acc8(u2, s, q); acc8(u3, s, q);
+    for (; k + 8 <= n; k += 8) {
+      const uint64_t pol = k >= k_keep ? pol_keep : pol_drop;
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = ld16_hint(ptr + j * stride, pol);
+      ptr += 8 * stride;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc8(u[j], s, q);
     }
-    for (; k < n; ++k, ptr += stride) acc8(__ldg(reinterpret_cast<const uint4*>(ptr)), s, q);
+    for (; k < n; ++k, ptr += stride) acc8(ld16_hint(ptr, pol_keep), s, q);
     if (active) {
       float* ss = sm + (size_t)r * ct + ch;
       float* sq = sm + (size_t)(R + r) * ct + ch;
@@ -327,42 +347,43 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
     __nv_bfloat16* dst = out + ((long long)b * hw + p0 + r + (n - 1) * R) * ct + ch;
     auto run = [&](auto silu_tag) {
       constexpr bool kSilu = decltype(silu_tag)::value;
+      const uint64_t pol = l2_policy(keep_frac < 0.f ? 0 : 2);
       long long k = 0;
-      for (; k + 4 <= n; k += 4) {
-        const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(ptr));
-        const uint4 u1 = __ldcs(reinterpret_cast<const uint4*>(ptr - stride));
-        const uint4 u2 = __ldcs(reinterpret_cast<const uint4*>(ptr - 2 * stride));
-        const uint4 u3 = __ldcs(reinterpret_cast<const uint4*>(ptr - 3 * stride));
-        *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(u0, a, sft);
-        *reinterpret_cast<uint4*>(dst - ostride) = norm8<kSilu>(u1, a, sft);
-        *reinterpret_cast<uint4*>(dst - 2 * ostride) = norm8<kSilu>(u2, a, sft);
-        *reinterpret_cast<uint4*>(dst - 3 * ostride) = norm8<kSilu>(u3, a, sft);
+      uint4 u[4], w[4];
+      if (n >= 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = ld16_hint(ptr - j * stride, pol);
+      }
+      for (; k + 8 <= n; k += 4) {                  // the next batch's loads are in flight while this one is normalised
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = ld16_hint(ptr - (4 + j) * stride, pol);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst - j * ostride) = norm8<kSilu>(u[j], a, sft);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) u[j] = w[j];
         ptr -= 4 * stride;
         dst -= 4 * ostride;
       }
-      for (; k < n; ++k, ptr -= stride, dst -= ostride)
-        *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(__ldcs(reinterpret_cast<const uint4*>(ptr)), a, sft);
+      if (k + 4 <= n) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst - j * ostride) = norm8<kSilu>(u[j], a, sft);
+        ptr -= 4 * stride;
+        dst -= 4 * ostride;
+        k += 4;
+      }
+      for (; k < n; ++k, ptr -= stride, dst -= ostride) *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(ld16_hint(ptr, pol), a, sft);
     };
     if (silu) run(std::true_type{}); else run(std::false_type{});
   }
 }
 
+// (Measured and dropped: the same kernel in packed fp32x2 arithmetic - 4 instead of 7.5 lane-instructions per element - was
+// no faster inside the tile-step graph (25.9 vs 25.0 us per launch) and slower for 640-wide rows (register pressure: 94-118
+// registers, two CTAs per SM); the bulk-copy pipelined variant below is slower still.  Both are kept out of the default path.)
 // one warp per PAIR of rows (both rows' loads are issued before either reduction: twice the bytes in flight per warp);
-// cols <= 1280 (5 vectors of 8 per lane); sum, then a mean-shifted second moment, in packed fp32x2 arithmetic: 4 instead of
-// 7.5 lane-instructions per element (at HBM speed an SM has to retire ~11 elements per clock out of 128 issue slots)
-__device__ __forceinline__ uint64_t ln_bf2_f2(uint32_t u) { return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
-__device__ __forceinline__ float ln_hsum(uint64_t v) {
-  float lo, hi;
-  unpack_f2(v, lo, hi);
-  return lo + hi;
-}
-__device__ __forceinline__ uint32_t ln_out2(uint64_t d, uint64_t rs, uint64_t g, uint64_t b) {
-  float lo, hi;
-  unpack_f2(fma_f2(d, mul_f2(rs, g), b), lo, hi);
-  return pack_bf16(lo, hi);
-}
+// cols <= 1280 (5 vectors of 8 per lane); single-pass sum / sum-of-squares in fp32 with a mean-shifted second moment
 template <int NV>
-__global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) layernorm_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                                                         long long rows, int cols, float eps) {
   pdl_launch_dependents();
@@ -373,43 +394,41 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_kernel(const
   if (row0 >= rows) return;
   const bool has1 = row0 + 1 < rows;
   const int V = cols >> 3;
-  const float inv_cols = 1.f / (float)cols;
-  uint64_t f0[NV][4], f1[NV][4];
-  uint64_t s0 = 0ull, s1 = 0ull;
+  float f[2][NV][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < V && (r == 0 || has1)) load8(x + (row0 + r) * cols + v * 8, f[r][i]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[r][i][j] = 0.f;
+      }
+    }
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s0 += f[0][i][j]; s1 += f[1][i][j]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+  const float m0 = s0 / cols, m1 = s1 / cols;
+  float q0 = 0.f, q1 = 0.f;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
-    uint4 u0 = make_uint4(0u, 0u, 0u, 0u), u1 = make_uint4(0u, 0u, 0u, 0u);
     if (v < V) {
-      u0 = __ldg(reinterpret_cast<const uint4*>(x + row0 * cols + v * 8));
-      if (has1) u1 = __ldg(reinterpret_cast<const uint4*>(x + (row0 + 1) * cols + v * 8));
-    }
-    f0[i][0] = ln_bf2_f2(u0.x); f0[i][1] = ln_bf2_f2(u0.y); f0[i][2] = ln_bf2_f2(u0.z); f0[i][3] = ln_bf2_f2(u0.w);
-    f1[i][0] = ln_bf2_f2(u1.x); f1[i][1] = ln_bf2_f2(u1.y); f1[i][2] = ln_bf2_f2(u1.z); f1[i][3] = ln_bf2_f2(u1.w);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s0 = add_f2(s0, f0[i][j]); s1 = add_f2(s1, f1[i][j]); }
-  }
-  float m0 = ln_hsum(s0), m1 = ln_hsum(s1);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { m0 += __shfl_xor_sync(0xffffffffu, m0, o); m1 += __shfl_xor_sync(0xffffffffu, m1, o); }
-  m0 *= inv_cols; m1 *= inv_cols;
-  const uint64_t nm0 = pack_f2(-m0, -m0), nm1 = pack_f2(-m1, -m1);
-  uint64_t q0 = 0ull, q1 = 0ull;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    if (lane + 32 * i < V) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        f0[i][j] = add_f2(f0[i][j], nm0); q0 = fma_f2(f0[i][j], f0[i][j], q0);
-        f1[i][j] = add_f2(f1[i][j], nm1); q1 = fma_f2(f1[i][j], f1[i][j], q1);
+      for (int j = 0; j < 8; ++j) {
+        const float d0 = f[0][i][j] - m0, d1 = f[1][i][j] - m1;
+        q0 += d0 * d0; q1 += d1 * d1;
       }
     }
   }
-  float v0 = ln_hsum(q0), v1 = ln_hsum(q1);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, o); v1 += __shfl_xor_sync(0xffffffffu, v1, o); }
-  const float rs0 = rsqrtf(v0 * inv_cols + eps), rs1 = rsqrtf(v1 * inv_cols + eps);
-  const uint64_t r0p = pack_f2(rs0, rs0), r1p = pack_f2(rs1, rs1);
+  for (int o = 16; o > 0; o >>= 1) { q0 += __shfl_xor_sync(0xffffffffu, q0, o); q1 += __shfl_xor_sync(0xffffffffu, q1, o); }
+  const float rs0 = rsqrtf(q0 / cols + eps), rs1 = rsqrtf(q1 / cols + eps);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = lane + 32 * i;
@@ -418,21 +437,19 @@ __global__ void __launch_bounds__(256, (NV <= 3 ? 3 : 2)) layernorm_kernel(const
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      const uint64_t gg[4] = {pack_f2(g0.x, g0.y), pack_f2(g0.z, g0.w), pack_f2(g1.x, g1.y), pack_f2(g1.z, g1.w)};
-      const uint64_t bb[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
-      uint4 y;
-      y.x = ln_out2(f0[i][0], r0p, gg[0], bb[0]); y.y = ln_out2(f0[i][1], r0p, gg[1], bb[1]);
-      y.z = ln_out2(f0[i][2], r0p, gg[2], bb[2]); y.w = ln_out2(f0[i][3], r0p, gg[3], bb[3]);
-      *reinterpret_cast<uint4*>(out + row0 * cols + v * 8) = y;
-      if (has1) {
-        y.x = ln_out2(f1[i][0], r1p, gg[0], bb[0]); y.y = ln_out2(f1[i][1], r1p, gg[1], bb[1]);
-        y.z = ln_out2(f1[i][2], r1p, gg[2], bb[2]); y.w = ln_out2(f1[i][3], r1p, gg[3], bb[3]);
-        *reinterpret_cast<uint4*>(out + (row0 + 1) * cols + v * 8) = y;
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o0[8], o1[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o0[j] = (f[0][i][j] - m0) * rs0 * gg[j] + bb[j];
+        o1[j] = (f[1][i][j] - m1) * rs1 * gg[j] + bb[j];
       }
+      store8(out + row0 * cols + v * 8, o0);
+      if (has1) store8(out + (row0 + 1) * cols + v * 8, o1);
     }
   }
 }
-
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm, persistent + bulk-copy pipelined.  A producer thread streams blocks of 16 contiguous rows into a 5-stage
 // shared-memory ring with ONE cp.async.bulk each (the rows of a block are contiguous in memory) completing on an mbarrier;
@@ -611,11 +628,11 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
   FD_REQUIRE(x0 && out && work && gamma && beta, "fd_groupnorm_nhwc_fused: null pointer");
   FD_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0 && ct % groups == 0 && groups <= 64, "fd_groupnorm_nhwc_fused: channels %d+%d groups %d unsupported", c0, c1, groups);
   const int V = ct / 8;
-  int R = 512 / (V > 0 ? V : 1);
+  int R = kGnFusedThreads / (V > 0 ? V : 1);
   if (R < 1) R = 1;
   const int threads = ((V * R + 31) / 32) * 32;
   const size_t smem = (size_t)2 * R * ct * sizeof(float);
-  if (!sync || !gn_fused_enabled() || V > 512 || threads > 512 || batch > kGnSyncMaxBatch || smem > 48 * 1024 || hw < 1)
+  if (!sync || !gn_fused_enabled() || V > kGnFusedThreads || threads > kGnFusedThreads || batch > kGnSyncMaxBatch || smem > 48 * 1024 || hw < 1)
     return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
   // co-resident CTA slots (cached per launch shape)
   static int occ_cache[17][13];                         // [threads/32][smem/4096]
@@ -632,9 +649,14 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
   if (cps < 1) return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
   if (cps > hw) cps = (int)hw;
   float* partial = work;
+  static int l2hint = -1;
+  if (l2hint < 0) { const char* e = getenv("FD_GN_L2HINT"); l2hint = (e && e[0] == '0') ? 0 : 1; }
+  // L2 budget for the re-read: ~56 MB of the 126 MB (both dies hold a copy of far lines; the output stream needs room too)
+  const double tensor_bytes = (double)batch * hw * ct * 2.0;
+  const float keep_frac = !l2hint ? -1.f : (tensor_bytes <= 56e6 ? 1.f : (float)(56e6 / tensor_bytes));
   gn_fused_kernel<<<dim3(cps * batch), dim3(threads), smem, stream>>>(
       (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
-      (__nv_bfloat16*)out, partial, (unsigned*)sync, batch, cps);
+      (__nv_bfloat16*)out, partial, (unsigned*)sync, batch, cps, keep_frac);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -53,7 +53,7 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
     return out
 
 
-def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0):
+def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0, alpha=1.0):
     """3x3 conv on NHWC bf16 x [B,H,W,C] (optionally channel-concatenated with x2); w packed [N, 9*(C+C2)]."""
     assert x.dim() == 4 and x.dtype == BF16 and x.stride(3) == 1
     B, H, W, C0 = x.shape
@@ -84,7 +84,7 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
     if residual is not None:
         assert residual.dtype == BF16 and residual.stride(3) == 1
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(2)
-    d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(2), 1.0, block_n
+    d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(2), alpha, block_n
     check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(conv)")
     return out
 
@@ -142,6 +142,19 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None):
         out = torch.empty_like(x)
     cols = x.shape[-1]
     check(lib.fd_layernorm(_p(x), _p(gamma), _p(beta), _p(out), x.numel() // cols, cols, eps, _stream()), "fd_layernorm")
+    return out
+
+
+def axpby(a, b, alpha, beta, out):
+    """out = alpha*a + beta*b on bf16 tensors whose last dim has unit stride and whose leading dims collapse to one row pitch
+    (NHWC tensors or channel-slice views of them)."""
+    for t in (a, b, out):
+        assert t.dtype == BF16 and t.stride(-1) == 1 and t.shape == a.shape
+        assert all(t.stride(i) == t.stride(i + 1) * t.shape[i + 1] for i in range(t.dim() - 2)), "rows must share one pitch"
+    cols = a.shape[-1]
+    rows = a.numel() // cols
+    check(lib.fd_axpby_bf16(_p(a), a.stride(-2), _p(b), b.stride(-2), _p(out), out.stride(-2), rows, cols, alpha, beta, _stream()),
+          "fd_axpby_bf16")
     return out
 
 

@@ -42,7 +42,7 @@ typedef struct fd_gemm_desc {
   int32_t batch, in_h, in_w; /* conv input geometry                                                       */
   int32_t pad_lo;        /* zero padding at top/left (1: pad=1; 0: the VAE's F.pad(0,1,0,1) + pad 0)      */
   int32_t act;           /* 0 none, 1 SiLU, 2 GEGLU (B rows interleaved h0,g0,h1,g1… → N/2 outputs), 3 QuickGELU, */
-                         /* 4 GELU (erf form; OpenCLIP-bigG text encoder MLP)                                   */
+                         /* 4 GELU (erf form; OpenCLIP-bigG text encoder MLP), 5 LeakyReLU(0.2) (BSRNet)        */
   int32_t bias_along_m;  /* bias indexed by output row instead of column                                  */
   int32_t out_fp32;      /* out dtype: 0 bf16, 1 fp32                                                     */
   const float* bias;     /* [N] (or [M]) fp32, or NULL                                                    */
@@ -103,6 +103,10 @@ int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x1, int32_t 
  * FaithDiff LayerNorm (…extension.py:229-235).                                                             */
 int fd_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t rows, int32_t cols, float eps,
                  void* stream);
+/* out[r, :cols] = alpha * a[r, :cols] + beta * b[r, :cols] on bf16 row views with independent pitches (elements; cols and
+ * pitches multiples of 8, 16-byte aligned) — the `out * 0.2 + x` of RRDB (bsrnet_arch.py:72) on channel-slice views.   */
+int fd_axpby_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo, int64_t rows, int32_t cols,
+                  float alpha, float beta, void* stream);
 /* nearest-neighbour resize NHWC (Upsample2D before its conv: oh=2h, ow=2w, or the `upsample_size` path) */
 int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch, int32_t h, int32_t w, int32_t oh, int32_t ow,
                              int32_t c, void* stream);

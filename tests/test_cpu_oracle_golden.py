@@ -128,3 +128,22 @@ def test_check_image_size_and_mha_identity():
     y2 = blk(torch.cat([x, x], 0))
     y1 = blk(x)
     assert torch.allclose(y2[0], y1[0], atol=1e-6) and torch.allclose(y2[1], y1[0], atol=1e-6)
+
+
+def test_bsrnet_oracle_reproduces_reference_golden(golden_dir):
+    """oracle/bsrnet_oracle.py against the outputs of the reference's own RRDBNet (bsrnet_arch.py run by
+    oracle/make_golden_bsrnet.py): bit-exact on this torch build, forward and tiled deg_remove; parameter count known answer."""
+    import numpy as np
+    from oracle import bsrnet_oracle as B
+    g = np.load(os.path.join(golden_dir, "bsrnet.npz"))
+    assert int(g["n_params_full"]) == 16697987 == sum(int(np.prod(s)) for s in B.param_shapes().values())
+    cfg = dict(in_nc=3, out_nc=3, nf=64, nb=2, gc=32, sf=4)
+    sd = B.random_state_dict(seed=11, **cfg)
+    with torch.no_grad():
+        for case in ("fwd_a", "fwd_ragged", "fwd_batch2"):
+            y = B.forward(sd, torch.from_numpy(g[case + "_x"]))
+            assert torch.allclose(y, torch.from_numpy(g[case + "_y"]), rtol=0, atol=2e-6), case
+        for case in ("deg_a", "deg_ragged", "deg_one_tile"):
+            ts, tp = (int(v) for v in g[case + "_tile"])
+            y = B.deg_remove(sd, torch.from_numpy(g[case + "_x"]), tile_size=ts, tile_pad=tp)
+            assert torch.allclose(y, torch.from_numpy(g[case + "_y"]), rtol=0, atol=2e-6), case

@@ -79,6 +79,35 @@ def test_conv3x3(ops, B, H, W, C0, C1, N, stride, pad_lo):
     assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,act,alpha,res", [(64, 32, 5, 1.0, False), (96, 32, 5, 1.0, False), (160, 32, 5, 1.0, False),
+                                                    (192, 64, 0, 0.2, True), (128, 32, 0, 1.0, False)])
+def test_conv3x3_channel_slice_views(ops, cin, cout, act, alpha, res):
+    """BSRNet dense-block convs: the input is the first `cin` channels of a 192-wide NHWC buffer (strided TMA view, K per tap
+    not a multiple of 64), the output a channel slice of another buffer; LeakyReLU(0.2) / alpha + residual epilogues."""
+    torch.manual_seed(cin + cout)
+    B, H, W = 2, 20, 28
+    buf = torch.randn(B, H, W, 192, device="cuda").to(BF)
+    dst = torch.zeros(B, H, W, 192, device="cuda", dtype=BF)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / (9 * cin) ** 0.5).to(BF)
+    b = torch.randn(cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    lo = 64 if cout == 32 else 0
+    out = dst[..., lo:lo + cout]
+    ops.conv3x3(buf[..., :cin], wp, bias=b, act=act, alpha=alpha, residual=buf[..., :cout] if res else None, out=out)
+    ref = F.conv2d(buf[..., :cin].permute(0, 3, 1, 2).float(), w.float(), None, padding=1) * alpha + b[None, :, None, None]
+    if act == 5:
+        ref = F.leaky_relu(ref, 0.2)
+    if res:
+        ref = ref + buf[..., :cout].permute(0, 3, 1, 2).float()
+    assert rel(out.permute(0, 3, 1, 2), ref) < 5e-3
+    mask = torch.ones(192, dtype=torch.bool, device="cuda"); mask[lo:lo + cout] = False
+    assert dst[..., mask].abs().max() == 0                      # nothing outside the slice was written
+    # axpby on slice views
+    o2 = torch.zeros_like(dst)
+    ops.axpby(dst[..., lo:lo + cout], buf[..., :cout], 0.2, 1.0, out=o2[..., :cout])
+    assert rel(o2[..., :cout], 0.2 * dst[..., lo:lo + cout].float() + buf[..., :cout].float()) < 4e-3
+
+
 @pytest.mark.parametrize("B,heads,lq,lk", [(2, 2, 256, 256), (2, 10, 4096, 4096), (2, 4, 1024, 77), (1, 1, 16, 16), (2, 3, 200, 333),
                                            (3, 20, 1000, 77), (1, 2, 2048, 128)])
 def test_attention_d64(ops, B, heads, lq, lk):
