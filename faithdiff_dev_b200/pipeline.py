@@ -244,10 +244,16 @@ class FaithDiffStableDiffusionXLPipeline:
         """VaeImageProcessor.preprocess (pipeline…:1246): host u8 → pinned → H2D → kernel."""
         if isinstance(lr_img, PIL.Image.Image):
             w, h = width - width % 8, height - height % 8
-            if lr_img.size != (w, h):
-                lr_img = lr_img.resize((w, h), resample=PIL.Image.LANCZOS)
             arr = np.asarray(lr_img.convert("RGB"), dtype=np.uint8)
             host = torch.from_numpy(np.ascontiguousarray(arr))
+            if lr_img.size != (w, h):
+                # VaeImageProcessor.resize (PIL LANCZOS) on the GPU, bit-identical to PIL (fd_resample_u8_*): the smaller
+                # source image is what crosses PCIe
+                from .image_process import resize_lanczos
+                self._h2d_bytes = host.numel()
+                dev = resize_lanczos(host.pin_memory(), (w, h), device=self.device)
+                self._last_input_u8 = dev
+                return ops.image_preprocess(dev)[0], dev
         else:
             host = lr_img            # HWC uint8 tensor (host, ideally pinned)
         if not host.is_cuda:

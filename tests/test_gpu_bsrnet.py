@@ -1,6 +1,7 @@
 """-m gpu: BSRNet pre-clean (RRDBNet) on the B200 kernels against (a) the REAL reference's outputs stored in
 tests/golden/bsrnet.npz (FaithDiff/models/bsrnet_arch.py run by oracle/make_golden_bsrnet.py) and (b) the oracle
-restatement on fresh inputs.  bf16 activations vs the reference's fp32: rel-L2 <= 1.5e-2 and PSNR >= 40 dB on the image."""
+restatement on fresh inputs.  bf16 activations vs the reference's fp32: rel-L2 <= 1.5e-2 and PSNR >= 45 dB relative to the output's value range
+(measured on B200: rel-L2 5.4e-3 at nb=2, 9.6e-3 at nb=23)."""
 import os
 
 import numpy as np
@@ -19,7 +20,9 @@ def rel(a, b):
 
 
 def psnr(a, b):
-    return (10 * torch.log10(1.0 / ((a.float() - b.float()) ** 2).mean().clamp_min(1e-20))).item()
+    """PSNR against the reference's own value range (random-init weights do not produce [0,1] images)."""
+    rng = (b.float().max() - b.float().min()).clamp_min(1e-20)
+    return (10 * torch.log10(rng ** 2 / ((a.float() - b.float()) ** 2).mean().clamp_min(1e-30))).item()
 
 
 @pytest.fixture(scope="module")
@@ -36,7 +39,7 @@ def test_forward_matches_reference_golden(net, case):
     x, y = torch.from_numpy(g[case + "_x"]), torch.from_numpy(g[case + "_y"])
     out = net(x.cuda())
     assert out.shape == y.shape and out.dtype == torch.float32
-    assert rel(out.cpu(), y) < 1.5e-2 and psnr(out.cpu(), y) > 40.0, (rel(out.cpu(), y), psnr(out.cpu(), y))
+    assert rel(out.cpu(), y) < 1.5e-2 and psnr(out.cpu(), y) > 45.0, (rel(out.cpu(), y), psnr(out.cpu(), y))
 
 
 @pytest.mark.parametrize("case", ["deg_a", "deg_ragged", "deg_one_tile"])
@@ -46,7 +49,7 @@ def test_deg_remove_matches_reference_golden(net, case):
     ts, tp = (int(v) for v in g[case + "_tile"])
     out = net.deg_remove(x.cuda(), tile_size=ts, tile_pad=tp)
     assert out.shape == y.shape
-    assert rel(out.cpu(), y) < 1.5e-2 and psnr(out.cpu(), y) > 40.0, (rel(out.cpu(), y), psnr(out.cpu(), y))
+    assert rel(out.cpu(), y) < 1.5e-2 and psnr(out.cpu(), y) > 45.0, (rel(out.cpu(), y), psnr(out.cpu(), y))
 
 
 def test_full_depth_network_and_default_tiling():
@@ -60,7 +63,7 @@ def test_full_depth_network_and_default_tiling():
     x = torch.rand(1, 3, 40, 530, generator=torch.Generator().manual_seed(1))
     ref = B.deg_remove(sd, x)
     out = n.deg_remove(x.cuda())
-    assert rel(out.cpu(), ref) < 2e-2 and psnr(out.cpu(), ref) > 38.0, (rel(out.cpu(), ref), psnr(out.cpu(), ref))
+    assert rel(out.cpu(), ref) < 2e-2 and psnr(out.cpu(), ref) > 42.0, (rel(out.cpu(), ref), psnr(out.cpu(), ref))
 
 
 def test_errors():
