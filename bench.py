@@ -305,7 +305,7 @@ def main():
     W, H = wl["lq"][0] * wl["scale"], wl["lq"][1] * wl["scale"]
     up = lq.resize((W, H), Image.LANCZOS)
     assert W % 8 == 0 and H % 8 == 0
-    host_u8 = torch.from_numpy(np.ascontiguousarray(np.asarray(up, dtype=np.uint8))).pin_memory()
+    host_u8 = torch.from_numpy(np.array(up, dtype=np.uint8)).pin_memory()
     dev_u8 = host_u8.cuda()
     host_out = torch.empty((H, W, 3), dtype=torch.uint8).pin_memory()
     g = torch.Generator().manual_seed(7)

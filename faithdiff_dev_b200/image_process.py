@@ -93,10 +93,10 @@ def _device_tables(in_w, in_h, out_w, out_h, device):
             row0 = int(vb[0, 0])
             rows = int(vb[-1, 0] + vb[-1, 1]) - row0
             vb = vb - np.array([row0, 0], np.int32)
-        vert = (torch.from_numpy(np.ascontiguousarray(vb)).to(device), torch.from_numpy(np.ascontiguousarray(vk)).to(device))
+        vert = (torch.from_numpy(np.array(vb)).to(device), torch.from_numpy(np.array(vk)).to(device))
     if out_w != in_w:
         hb, hk = resample_taps(in_w, out_w)
-        horiz = (torch.from_numpy(np.ascontiguousarray(hb)).to(device), torch.from_numpy(np.ascontiguousarray(hk)).to(device))
+        horiz = (torch.from_numpy(np.array(hb)).to(device), torch.from_numpy(np.array(hk)).to(device))
     return horiz, vert, row0, rows
 
 

@@ -243,3 +243,37 @@ def test_lanczos_tap_table_properties():
         resize_lanczos(np.zeros((8, 8, 3), np.uint8), (16, 16), device="cpu")   # no CPU path
     with pytest.raises(ValueError):
         resize_lanczos(np.zeros((8, 8, 3), np.float32), (16, 16))
+
+
+def test_bench_tile_count_matches_the_tile_walk():
+    """bench.count_tiles (used to scale the CPU sample) against the product's LocalAttention walk for every workload."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from faithdiff_dev_b200.tiling import tile_origins
+    for name, want in (("4k", 28), ("1k", 1), ("batch32", 9), ("tiny", 1)):
+        wl = bench.workload(name)
+        h, w = wl["lq"][1] * wl["scale"] // 8, wl["lq"][0] * wl["scale"] // 8
+        assert bench.count_tiles(wl) == len(tile_origins(h, w, 128, 128, 0.5)[0]) == want
+
+
+def test_bsrnet_host_logic():
+    """RRDBNet keeps the reference's state-dict key set (bsrnet_arch.py:38-43, :82-92) and argument checks; no GPU needed."""
+    import faithdiff_dev_b200 as fd
+    from oracle import bsrnet_oracle as B
+    net = fd.RRDBNet(in_nc=3, out_nc=3, nf=64, nb=23, gc=32, sf=4)
+    assert net.expected_keys() == sorted(B.param_shapes())
+    assert fd.RRDBNet(nb=2, sf=2).expected_keys() == sorted(B.param_shapes(nb=2, sf=2))
+    with pytest.raises(ValueError):
+        fd.RRDBNet(sf=3)
+    with pytest.raises(NotImplementedError):
+        fd.RRDBNet(in_nc=1)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            net.load_state_dict({})                      # no CUDA device: fails loudly, no CPU path
+        with pytest.raises(RuntimeError):
+            net.deg_remove(torch.zeros(1, 3, 8, 8))
+    # the tile plan of deg_remove is the reference's (checked bit-exactly through the golden outputs on the GPU); its geometry:
+    plan = B.tile_plan(40, 530)
+    assert [(p[2], p[3], p[6], p[7]) for p in plan] == [(0, 512, 0, 528), (512, 530, 496, 530)]
