@@ -170,3 +170,21 @@ def test_lanczos_resize_bit_exact_vs_pil(fd, w, h, ow, oh, mode):
     assert torch.equal(resize_lanczos(torch.from_numpy(a).cuda(), (ow, oh)), got)
     with pytest.raises(ValueError):                  # PIL premultiplies alpha for RGBA: not this kernel's contract
         resize_lanczos(Image.new("RGBA", (8, 8)), (16, 16))
+
+
+def test_pipeline_preprocess_resizes_like_pil(fd):
+    """VaeImageProcessor.preprocess (pipeline…:1246) resizes a PIL input to (width, height) with LANCZOS before normalising;
+    the pipeline does that resize on the GPU: same u8 image as PIL's, same normalised tensor as the oracle's arithmetic."""
+    import types
+    from PIL import Image
+    a = np.random.default_rng(3).integers(0, 256, size=(40, 56, 3), dtype=np.uint8)
+    img = Image.fromarray(a)
+    fake = types.SimpleNamespace(device=torch.device("cuda"))
+    nhwc, dev = fd.FaithDiffStableDiffusionXLPipeline._preprocess(fake, img, 80, 112)
+    ref_u8 = np.asarray(img.resize((112, 80), Image.LANCZOS))
+    assert np.array_equal(dev.cpu().numpy(), ref_u8) and fake._h2d_bytes == a.size
+    ref = (torch.from_numpy(ref_u8.copy()).float() / 255.0) * 2.0 - 1.0
+    assert torch.equal(nhwc[0].float().cpu(), ref.to(BF).float())
+    # same size: no resize, the u8 image itself is uploaded
+    nhwc2, dev2 = fd.FaithDiffStableDiffusionXLPipeline._preprocess(fake, img, 40, 56)
+    assert np.array_equal(dev2.cpu().numpy(), a)
