@@ -37,6 +37,28 @@ struct __align__(8) AttnBars {
   uint32_t tmem_base;
 };
 
+// exp2 on the FMA pipe for a PAIR of arguments (opt-in, FD_ATTN_POLY): the softmax of this kernel is paced by the 16-lane MUFU
+// pipe (128 ex2 per query row and key block against 512 MMA cycles), so part of the exponentials can move to the otherwise idle
+// FMA pipe: a is clamped to >= -125, split with the 1.5*2^23 magic-number rounding into n = rint(a) and f = a - n in [-0.5, 0.5],
+// 2^f is a degree-3 polynomial (Lawson-fitted, max relative error 7.6e-5 = 1/50 of the bf16 rounding step P goes through),
+// and n is added into the exponent field with one integer multiply-add.  6 packed fp32x2 + 2 max + 2 integer ops per pair.
+__device__ __forceinline__ void exp2_pair_poly(float a0, float a1, float& e0, float& e1) {
+  const uint64_t a = pack_f2(fmaxf(a0, -125.f), fmaxf(a1, -125.f));
+  const uint64_t t = add_f2(a, pack_f2(12582912.f, 12582912.f));
+  const uint64_t n = add_f2(t, pack_f2(-12582912.f, -12582912.f));
+  const uint64_t f = fma_f2(n, pack_f2(-1.f, -1.f), a);
+  uint64_t q = fma_f2(pack_f2(0.05520550534129143f, 0.05520550534129143f), f, pack_f2(0.24261397123336792f, 0.24261397123336792f));
+  q = fma_f2(q, f, pack_f2(0.6932547688484192f, 0.6932547688484192f));
+  q = fma_f2(q, f, pack_f2(0.9999276995658875f, 0.9999276995658875f));
+  float q0, q1, t0, t1;
+  unpack_f2(q, q0, q1);
+  unpack_f2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(t0) * 8388608 + __float_as_int(q0));     // (bits(t) << 23) + bits(2^f); bits(magic) << 23 == 0
+  e1 = __int_as_float(__float_as_int(t1) * 8388608 + __float_as_int(q1));
+}
+
+// kPolyOf8: of every 8 consecutive pairs of a row, the first kPolyOf8 use exp2_pair_poly, the rest MUFU ex2 (0 = all MUFU)
+template <int kPolyOf8>
 __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
@@ -208,8 +230,17 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
             const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), scale2, nmxs2);
             float a0, a1;
             unpack_f2(t, a0, a1);
-            a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower, twice: the extra
-            a1 = fast_exp2(a1);      //  converts cost more issue slots than the halved MUFU count saves)
+            if constexpr (kPolyOf8 > 0) {
+              if (((i >> 1) & 7) < kPolyOf8) {          // compile-time after unrolling
+                exp2_pair_poly(a0, a1, a0, a1);
+              } else {
+                a0 = fast_exp2(a0);
+                a1 = fast_exp2(a1);
+              }
+            } else {
+              a0 = fast_exp2(a0);      // (an f16x2 exp2 — two results per MUFU op — was measured slower, twice: the extra
+              a1 = fast_exp2(a1);      //  converts cost more issue slots than the halved MUFU count saves)
+            }
             if constexpr (!kFull) {
               if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
               if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
@@ -517,7 +548,10 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
   const size_t smem_short = 7 * kTile + sizeof(AttnShortBars);
   static bool attr = false;
   if (!attr) {
-    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_shortkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_short));
     attr = true;
   }
@@ -539,7 +573,13 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
     FD_CHECK_CUDA(launch_pdl(attention_d64_shortkv_kernel, grid, dim3(192), smem_short, stream, 1, p));
   } else {
     dim3 grid(nqb, heads, batch);
-    FD_CHECK_CUDA(launch_pdl(attention_d64_kernel, grid, dim3(192), smem_bytes, stream, 1, p));
+    // FD_ATTN_POLY = 2 / 3 / 4: that many of every 8 exponential pairs on the FMA pipe (opt-in; not yet measured on a GPU)
+    static int poly = -1;
+    if (poly < 0) { const char* e = getenv("FD_ATTN_POLY"); poly = e ? atoi(e) : 0; }
+    if (poly == 2) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<2>, grid, dim3(192), smem_bytes, stream, 1, p));
+    else if (poly == 3) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<3>, grid, dim3(192), smem_bytes, stream, 1, p));
+    else if (poly == 4) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<4>, grid, dim3(192), smem_bytes, stream, 1, p));
+    else FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<0>, grid, dim3(192), smem_bytes, stream, 1, p));
   }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
