@@ -159,9 +159,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // packed fp32x2 helpers (the kernel is otherwise bound by instruction issue, not by HBM: the scalar version with an IEEE
 // division in SiLU needed ~20 lane-instructions per element against the ~22 per element an SM can issue at HBM speed)
 __device__ __forceinline__ uint64_t bf2_f2(uint32_t u) { return pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
@@ -608,6 +605,7 @@ extern "C" int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int
   return 0;
 }
 
+// [0, 64): arrive counters, [128, 192): done counters (one pair per sample; the middle third is reserved)
 extern "C" int64_t fd_groupnorm_sync_bytes() { return (int64_t)3 * kGnSyncMaxBatch * sizeof(unsigned); }
 
 static bool gn_fused_enabled() {

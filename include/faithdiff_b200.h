@@ -91,10 +91,13 @@ int64_t fd_groupnorm_work_floats(int32_t batch, int32_t groups, int32_t channels
 int fd_groupnorm_nhwc(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
                       void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
                       void* stream);
-/* Same result from ONE persistent launch (per-sample arrive/ready flags in `sync`, second read of x from L2): the
- * path the UNet / VAE use.  sync: fd_groupnorm_sync_bytes() bytes of device memory, zeroed ONCE by the caller and then
- * left alone (the kernel recycles its counters); one buffer per stream that may run GroupNorm concurrently.  Falls back
- * to the three-launch fd_groupnorm_nhwc for shapes it does not cover (or sync == NULL, or FD_GN_FUSED=0).          */
+/* Same result (same statistics; SiLU through tanh.approx, relative error 2^-11 of the sigmoid) from ONE launch: every CTA
+ * reduces one pixel chunk of one sample, arrives on the sample's counter in `sync`, waits for the sample's other chunks,
+ * combines the partial sums itself and normalises its chunk, re-reading it from L2 (norm.cu) — the path the UNet / VAE use.
+ * sync: fd_groupnorm_sync_bytes() bytes of device memory, zeroed ONCE by the caller and then left alone (the kernel
+ * recycles its counters); one buffer per stream that may run GroupNorm concurrently.  The grid must be co-resident: do not
+ * run two of these concurrently on one device.  Falls back to the three-launch fd_groupnorm_nhwc for shapes it does not
+ * cover (more than 2560 channels or 64 samples), for sync == NULL, or with FD_GN_FUSED=0.                          */
 int64_t fd_groupnorm_sync_bytes(void);
 int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x1, int32_t c1, const float* gamma, const float* beta,
                             void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
