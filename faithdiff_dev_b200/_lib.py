@@ -22,6 +22,15 @@ class GemmDesc(C.Structure):
     ]
 
 
+class GemmLnDesc(C.Structure):
+    """fd_gemm_ln_desc (LayerNorm folded into the GEMMs around it; opt-in)."""
+    _fields_ = [
+        ("stats_in", C.c_void_p), ("stats_in_ld", C.c_int64), ("stats_in_n", C.c_int32), ("pad0_", C.c_int32),
+        ("colsum", C.c_void_p), ("inv_c", C.c_float), ("eps", C.c_float),
+        ("stats_out", C.c_void_p), ("stats_out_ld", C.c_int64), ("stats_out_n", C.c_int32), ("pad1_", C.c_int32),
+    ]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -40,6 +49,7 @@ lib.fd_colorfix_work_floats.restype = C.c_int64
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 _SIGS = {
     "fd_gemm": [C.POINTER(GemmDesc), vp],
+    "fd_gemm_ln": [C.POINTER(GemmDesc), C.POINTER(GemmLnDesc), vp],
     "fd_attention_d64": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
     "fd_attention_d64_causal": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
     "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
@@ -73,7 +83,7 @@ _SIGS = {
     "fd_adain_color_fix": [vp, vp, vp, i32, i32, vp, vp],
     "fd_wavelet_color_fix": [vp, vp, vp, i32, i32, vp, vp],
 }
-EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count", "fd_sizeof_gemm_desc"] + list(_SIGS)
+EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count", "fd_sizeof_gemm_desc", "fd_sizeof_gemm_ln_desc"] + list(_SIGS)
 for _n, _a in _SIGS.items():
     getattr(lib, _n).argtypes = _a
 
@@ -81,6 +91,11 @@ for _n, _a in _SIGS.items():
 if lib.fd_sizeof_gemm_desc() != C.sizeof(GemmDesc):
     raise ImportError("faithdiff_dev_b200: GemmDesc mirror (%d B) does not match fd_gemm_desc (%d B)"
                       % (C.sizeof(GemmDesc), lib.fd_sizeof_gemm_desc()))
+
+
+if lib.fd_sizeof_gemm_ln_desc() != C.sizeof(GemmLnDesc):
+    raise ImportError("faithdiff_dev_b200: GemmLnDesc mirror (%d B) does not match fd_gemm_ln_desc (%d B)"
+                      % (C.sizeof(GemmLnDesc), lib.fd_sizeof_gemm_ln_desc()))
 
 
 def check(status, what):

@@ -1,6 +1,8 @@
 """Host-side building blocks shared by the UNet, the LQ encoder and the VAE.  Each block owns weights already
 packed into the kernel layouts (bf16 K-major GEMM operands, fp32 biases / norm affine) and drives the C-ABI
 kernels over NHWC bf16 activations.  State-dict keys are the reference's (diffusers 0.28 naming)."""
+import os
+
 import torch
 
 from . import ops
@@ -142,6 +144,21 @@ def interleave_geglu(w, b):
     return wi, bi
 
 
+# FD_LN_FOLD=1 (opt-in, not the default path): the three LayerNorms of a transformer block are folded into the GEMMs around
+# them (fd_gemm_ln): no LayerNorm launch, no normalised copy of the residual stream
+LN_FOLD = os.environ.get("FD_LN_FOLD", "0") == "1"
+
+
+def fold_layernorm(w, bias, gamma, beta):
+    """(W [N,C] bf16, bias [N] fp32 or None, gamma, beta [C] fp32) -> (W' = bf16(W*gamma), colsum(W') fp32, bias + W beta)."""
+    wf = w.float()
+    wp = (wf * gamma[None, :]).to(BF16).contiguous()
+    bp = wf @ beta
+    if bias is not None:
+        bp = bp + bias
+    return wp, wp.float().sum(1).contiguous(), bp.float().contiguous()
+
+
 class TransformerBlock:
     """diffusers BasicTransformerBlock: LN→self-attn→+, LN→cross-attn(text)→+, LN→GEGLU FF→+."""
 
@@ -157,9 +174,28 @@ class TransformerBlock:
         self.wff2, self.bff2 = W.mat("ff.net.2.weight"), W.f32("ff.net.2.bias")
         self.C = self.wo1.shape[0]
         self.scale = (self.C // heads) ** -0.5
+        if LN_FOLD:
+            self.f_qkv = fold_layernorm(self.wqkv, None, *self.ln[0])
+            self.f_q2 = fold_layernorm(self.wq2, None, *self.ln[1])
+            self.f_ff1 = fold_layernorm(self.wff1, self.bff1, *self.ln[2])
 
     def text_kv(self, text2d):
         return ops.gemm(text2d, self.wkv2)
+
+    def call_folded(self, h, st, B, L, kv, lk):
+        """Same block with the LayerNorms folded away: `st` = RowStats of h from the GEMM that produced it; returns (h, st)."""
+        Cc = self.C
+        w, cs, b = self.f_qkv
+        qkv = ops.gemm(h, w, bias=b, ln_in=st, ln_colsum=cs)
+        a = ops.attention(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, self.heads, L, L, self.scale)
+        h, st = ops.gemm(a, self.wo1, bias=self.bo1, residual=h, stats_out=True)
+        w, cs, b = self.f_q2
+        q = ops.gemm(h, w, bias=b, ln_in=st, ln_colsum=cs)
+        a = ops.attention(q, kv[:, :Cc], kv[:, Cc:], B, self.heads, L, lk, self.scale)
+        h, st = ops.gemm(a, self.wo2, bias=self.bo2, residual=h, stats_out=True)
+        w, cs, b = self.f_ff1
+        g = ops.gemm(h, w, bias=b, act=2, ln_in=st, ln_colsum=cs)
+        return ops.gemm(g, self.wff2, bias=self.bff2, residual=h, stats_out=True)
 
     def __call__(self, h, B, L, kv, lk):
         Cc = self.C
@@ -194,8 +230,13 @@ class Transformer2D:
         B, H, Wd, Cc = x.shape
         L = H * Wd
         n = ops.groupnorm(x, self.ng, self.nb, self.groups, 1e-6, False)
-        h = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi)
-        for blk, kv in zip(self.blocks, kv_list):
-            h = blk(h, B, L, kv, lk)
+        if LN_FOLD:
+            h, st = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi, stats_out=True)
+            for blk, kv in zip(self.blocks, kv_list):
+                h, st = blk.call_folded(h, st, B, L, kv, lk)
+        else:
+            h = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi)
+            for blk, kv in zip(self.blocks, kv_list):
+                h = blk(h, B, L, kv, lk)
         out = ops.gemm(h, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc))
         return out.view(B, H, Wd, Cc)

@@ -43,6 +43,16 @@ struct GemmKParams {
   int act, bias_along_m, out_fp32;
   int tma_epi;         // 1: the epilogue moves residual and output through shared memory with TMA (bf16 output, 16 B aligned)
   int slot_bytes;      // bytes of one epilogue staging slot (a 32-row chunk of the output)
+  // LayerNorm folding (fd_gemm_ln, opt-in).  kLn = 2 (producer): per-row (sum, sum of squares) of the bf16-rounded output, one
+  // float2 slot per (n tile, chunk half).  kLn = 1 (consumer, A = the raw residual stream, B = W*gamma): the epilogue computes
+  // rstd_r * acc - rstd_r*mean_r * colsum[n] + bias'[n] from the producer's slots, i.e. LayerNorm(x) W^T + b without the
+  // LayerNorm pass.
+  const float2* ln_stats_in;
+  int ln_in_ld, ln_in_n;
+  const float* ln_colsum;
+  float ln_inv_c, ln_eps;
+  float2* ln_stats_out;
+  int ln_out_ld;
 };
 
 constexpr int kBlockM = 128;
@@ -78,7 +88,7 @@ __device__ __forceinline__ void raster_tile(int st, int m_super, int n_super, in
 
 // kPair = true instantiates the cta_group::2 (CTA-pair, UMMA M=256) variant; a kernel containing cta_group::2
 // instructions can only be launched with an even cluster size, hence two instantiations.
-template <bool kPair, int kEpi>
+template <bool kPair, int kEpi, int kLn = 0>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5;
@@ -248,6 +258,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
     const bool has_res = kEpi != 2 && p.residual != nullptr;
     const bool col_bias = p.bias && !bias_m_mode;
     float* bias_w = bars->bias_s[warp - 2];
+    float* csum_w = reinterpret_cast<float*>(bars + 1) + (warp - 2) * 128;   // kLn == 1: colsum strip (the host reserves these 4 KB)
     // TMA epilogue state: two staging slots per warp, used alternately by the running chunk sequence number `qseq`
     uint8_t* slot0 = slots + (size_t)(warp - 2) * 2 * p.slot_bytes;
     uint64_t* rbar = bars->res_full[warp - 2];
@@ -325,6 +336,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
         }
         __syncwarp();
       }
+      float ln_rstd = 0.f, ln_nrm = 0.f;            // kLn == 1: rstd and -rstd*mean of this thread's row
+      float ln_s1 = 0.f, ln_s2 = 0.f;               // kLn == 2: sum / sum of squares of this thread's row over its chunks of the tile
+      if constexpr (kLn == 1) {
+        __syncwarp();
+        int k = 0;
+        for (int c = chalf; c < nchunks; c += 2, ++k) {
+          const int n = ncol0 + c * 32 + lane;
+          csum_w[k * 32 + lane] = n < p.N ? __ldg(p.ln_colsum + n) : 0.f;
+        }
+        __syncwarp();
+        if (valid) {
+          const float2* sp = p.ln_stats_in + row * p.ln_in_ld;
+          float s1 = 0.f, s2 = 0.f;
+          for (int k2 = 0; k2 < p.ln_in_n; ++k2) {
+            const float2 t = __ldg(sp + k2);
+            s1 += t.x;
+            s2 += t.y;
+          }
+          const float mean = s1 * p.ln_inv_c;
+          const float var = fmaxf(fmaf(s2, p.ln_inv_c, -mean * mean), 0.f);
+          ln_rstd = rsqrtf(var + p.ln_eps);
+          ln_nrm = -ln_rstd * mean;
+        }
+      }
       mbar_wait(&bars->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * kAccCols;
@@ -333,8 +368,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
 
       // alpha, bias, per-sample row bias and activation on 8 consecutive columns n..n+7 (group g8 of the chunk)
       auto affine_act8 = [&](float (&x)[8], const uint32_t* v8, const float* bs8, int n) {
+        if constexpr (kLn == 1) {
+          const float* cs8 = csum_w + (bs8 - bias_w);
+          const float4 c0 = *reinterpret_cast<const float4*>(cs8);
+          const float4 c1 = *reinterpret_cast<const float4*>(cs8 + 4);
+          const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v8[j]) * p.alpha;
+          for (int j = 0; j < 8; ++j) x[j] = fmaf(__uint_as_float(v8[j]), ln_rstd, ln_nrm * cs[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v8[j]) * p.alpha;
+        }
         if (p.bias) {
           if (bias_m_mode) {
 #pragma unroll
@@ -370,8 +414,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
       auto geglu16 = [&](float (&o)[16], const uint32_t (&v)[32], const float* bs) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float h = __uint_as_float(v[2 * j]) * p.alpha;
-          float g = __uint_as_float(v[2 * j + 1]) * p.alpha;
+          float h, g;
+          if constexpr (kLn == 1) {
+            const float2 cs = *reinterpret_cast<const float2*>(csum_w + (bs - bias_w) + 2 * j);
+            h = fmaf(__uint_as_float(v[2 * j]), ln_rstd, ln_nrm * cs.x);
+            g = fmaf(__uint_as_float(v[2 * j + 1]), ln_rstd, ln_nrm * cs.y);
+          } else {
+            h = __uint_as_float(v[2 * j]) * p.alpha;
+            g = __uint_as_float(v[2 * j + 1]) * p.alpha;
+          }
           if (col_bias) {
             const float2 b = *reinterpret_cast<const float2*>(bs + 2 * j);
             h += b.x; g += b.y;
@@ -440,6 +491,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
               stv.x = pack_bf16(x[0], x[1]); stv.y = pack_bf16(x[2], x[3]);
               stv.z = pack_bf16(x[4], x[5]); stv.w = pack_bf16(x[6], x[7]);
               *sp = stv;
+              if constexpr (kLn == 2) {             // statistics of what the consumer will read: the ROUNDED values
+                float2 f;
+                f = unpack_bf16(stv.x); ln_s1 += f.x + f.y; ln_s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, ln_s2));
+                f = unpack_bf16(stv.y); ln_s1 += f.x + f.y; ln_s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, ln_s2));
+                f = unpack_bf16(stv.z); ln_s1 += f.x + f.y; ln_s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, ln_s2));
+                f = unpack_bf16(stv.w); ln_s1 += f.x + f.y; ln_s2 = fmaf(f.x, f.x, fmaf(f.y, f.y, ln_s2));
+              }
             }
           }
           fence_proxy_async();
@@ -457,6 +515,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           ++qseq;
         }
         if (chalf >= nchunks || ncol0 + chalf * 32 >= p.N) release_acc();   // this warp owned no chunk of the tile
+        if constexpr (kLn == 2) {
+          if (valid) p.ln_stats_out[row * p.ln_out_ld + n_blk * 2 + chalf] = make_float2(ln_s1, ln_s2);   // zeros if no chunk
+        }
       } else if constexpr (kEpi == 0) {
         // ---------------------------------------------------------------- direct epilogue (fp32 or unaligned output)
         auto process = [&](int c, const uint4 (&res)[4]) {
@@ -593,9 +654,12 @@ static void pick_patch(int H, int W, int* bw, int* bh) {
 
 using namespace fd;
 
-extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
+static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FD_REQUIRE(d && d->a[0] && d->b && d->out, "fd_gemm: null operand");
+  const bool ln_in = ln && ln->stats_in, ln_out = ln && ln->stats_out;
+  FD_REQUIRE(!(ln_in && ln_out), "fd_gemm_ln: one GEMM either consumes or produces row statistics");
+  FD_REQUIRE(!(ln_in || ln_out) || (d->mode == 0 && !d->a[1]), "fd_gemm_ln: plain single-source GEMMs only");
   FD_REQUIRE(d->mode >= 0 && d->mode <= 2, "fd_gemm: bad mode %d", d->mode);
   FD_REQUIRE(d->act >= 0 && d->act <= 5, "fd_gemm: bad act %d", d->act);
   GemmKParams p;
@@ -705,10 +769,11 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   }
   p.slot_bytes = d->act == 2 ? 1024 : 2048;
   const int staging_bytes = p.tma_epi ? 16 * p.slot_bytes : 0;
-  const int smem_budget = 227 * 1024 - (int)sizeof(PipeBarriers) - 64 - staging_bytes;
+  const int ln_strip_bytes = ln_in ? 8 * 128 * (int)sizeof(float) : 0;       // colsum strips of the 8 epilogue warps, after the barriers
+  const int smem_budget = 227 * 1024 - (int)sizeof(PipeBarriers) - 64 - staging_bytes - ln_strip_bytes;
   p.stages = smem_budget / stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  const size_t smem_bytes = (size_t)p.stages * stage_bytes + staging_bytes + sizeof(PipeBarriers);
+  const size_t smem_bytes = (size_t)p.stages * stage_bytes + staging_bytes + sizeof(PipeBarriers) + ln_strip_bytes;
 
   // tensor maps
   if (d->mode == 0) {
@@ -792,7 +857,22 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
     if (env_generic < 0) { const char* e = getenv("FD_GEMM_GENERIC_EPILOGUE"); env_generic = e ? atoi(e) : 0; }
     if (env_generic) epi = 0;
   }
+  if (ln_in) {
+    FD_REQUIRE(epi == 1 || epi == 2, "fd_gemm_ln: the consumer needs the TMA epilogue (bf16 output, act 0 or GEGLU)");
+    FD_REQUIRE(ln->colsum && ln->stats_in_n > 0 && ln->stats_in_ld >= ln->stats_in_n && ln->inv_c > 0.f, "fd_gemm_ln: bad consumer arguments");
+    FD_REQUIRE(d->alpha == 0.f || d->alpha == 1.f, "fd_gemm_ln: alpha is not applied on the consumer path");
+    p.ln_stats_in = (const float2*)ln->stats_in; p.ln_in_ld = (int)ln->stats_in_ld; p.ln_in_n = ln->stats_in_n;
+    p.ln_colsum = ln->colsum; p.ln_inv_c = ln->inv_c; p.ln_eps = ln->eps;
+  }
+  if (ln_out) {
+    FD_REQUIRE(epi == 1 && d->N % 32 == 0, "fd_gemm_ln: the producer needs the linear TMA epilogue and N %% 32 == 0");
+    FD_REQUIRE(ln->stats_out_ld >= 2 * p.n_tiles, "fd_gemm_ln: stats_out_ld %lld < %d slots", (long long)ln->stats_out_ld, 2 * p.n_tiles);
+    p.ln_stats_out = (float2*)ln->stats_out; p.ln_out_ld = (int)ln->stats_out_ld;
+    ln->stats_out_n = 2 * p.n_tiles;
+  }
   using KernelFn = void (*)(GemmKParams);
+  static const KernelFn kernels_ln[6] = {gemm_tcgen05_kernel<false, 1, 1>, gemm_tcgen05_kernel<false, 2, 1>, gemm_tcgen05_kernel<false, 1, 2>,
+                                         gemm_tcgen05_kernel<true, 1, 1>,  gemm_tcgen05_kernel<true, 2, 1>,  gemm_tcgen05_kernel<true, 1, 2>};
   static const KernelFn kernels[6] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
                                       gemm_tcgen05_kernel<true, 0>,  gemm_tcgen05_kernel<true, 1>,  gemm_tcgen05_kernel<true, 2>};
   static bool attr_set = false;
@@ -803,6 +883,14 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   const int csize = p.cm * p.cn;
   const int num_super = p.m_super * p.n_super;
   KernelFn kernel = kernels[(p.pair ? 3 : 0) + epi];
+  if (ln_in || ln_out) {
+    static bool ln_attr_set = false;
+    if (!ln_attr_set) {
+      for (int i = 0; i < 6; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels_ln[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      ln_attr_set = true;
+    }
+    kernel = kernels_ln[(p.pair ? 3 : 0) + (ln_out ? 2 : epi - 1)];
+  }
   if (csize == 1) {
     const int grid = num_super < sms ? num_super : sms;
     FD_CHECK_CUDA(launch_pdl(kernel, dim3(grid), dim3(kThreads), smem_bytes, stream, 1, p));
@@ -816,3 +904,9 @@ extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream_) {
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+extern "C" int fd_gemm(const fd_gemm_desc* d, void* stream) { return gemm_impl(d, nullptr, stream); }
+
+extern "C" int fd_gemm_ln(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream) { return gemm_impl(d, ln, stream); }
+
+extern "C" int32_t fd_sizeof_gemm_ln_desc(void) { return (int32_t)sizeof(fd_gemm_ln_desc); }

@@ -4,7 +4,7 @@ import ctypes as C
 
 import torch
 
-from ._lib import GemmDesc, check, lib
+from ._lib import GemmDesc, GemmLnDesc, check, lib
 
 BF16 = torch.bfloat16
 _DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
@@ -24,9 +24,19 @@ def _row_view(t):
     return t.data_ptr(), t.shape[1], t.stride(0)
 
 
+class RowStats:
+    """Per-row (sum, sum of squares) slots a producer GEMM leaves for the LayerNorm-folded consumer (fd_gemm_ln)."""
+    __slots__ = ("slots", "n")
+
+    def __init__(self, slots, n):
+        self.slots, self.n = slots, n          # fp32 [M, ld, 2] tensor; number of valid slots per row
+
+
 def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None, act=0, out=None, out_fp32=False,
-         alpha=1.0, bias_along_m=False, block_n=0):
-    """out[M,N] = epilogue(alpha * [a | a2] @ w^T).  a/a2: bf16 [M,K*] (unit inner stride); w: bf16 [N,K] contiguous."""
+         alpha=1.0, bias_along_m=False, block_n=0, ln_in=None, ln_colsum=None, ln_eps=1e-5, stats_out=False):
+    """out[M,N] = epilogue(alpha * [a | a2] @ w^T).  a/a2: bf16 [M,K*] (unit inner stride); w: bf16 [N,K] contiguous.
+    LayerNorm folding (opt-in): `stats_out=True` returns (out, RowStats of out); `ln_in=RowStats of a` with
+    `ln_colsum` = row sums of w (= W*gamma) computes LayerNorm(a) W^T + bias' without the LayerNorm pass."""
     d = GemmDesc()
     d.a[0], d.a_cols[0], d.a_ld[0] = _row_view(a)
     if a2 is not None:
@@ -49,8 +59,21 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
         assert residual.dtype == BF16 and residual.stride(1) == 1
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(0)
     d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(0), alpha, block_n
-    check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm")
-    return out
+    if ln_in is None and not stats_out:
+        check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm")
+        return out
+    ln = GemmLnDesc()
+    if ln_in is not None:
+        assert ln_colsum is not None and ln_colsum.dtype == torch.float32 and ln_colsum.numel() == N and a2 is None
+        assert ln_in.slots.shape[0] == M and ln_in.slots.dtype == torch.float32 and ln_in.slots.is_contiguous()
+        ln.stats_in, ln.stats_in_ld, ln.stats_in_n = ln_in.slots.data_ptr(), ln_in.slots.shape[1], ln_in.n
+        ln.colsum, ln.inv_c, ln.eps = ln_colsum.data_ptr(), 1.0 / a.shape[1], ln_eps
+    slots = None
+    if stats_out:
+        slots = torch.empty((M, 2 * ((N + 31) // 32), 2), device=a.device, dtype=torch.float32)
+        ln.stats_out, ln.stats_out_ld = slots.data_ptr(), slots.shape[1]
+    check(lib.fd_gemm_ln(C.byref(d), C.byref(ln), _stream()), "fd_gemm_ln")
+    return (out, RowStats(slots, ln.stats_out_n)) if stats_out else out
 
 
 def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0, alpha=1.0):

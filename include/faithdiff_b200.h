@@ -58,6 +58,30 @@ typedef struct fd_gemm_desc {
                          /* forces CTA-pair (cta_group::2) tiles, bit 13 forces single-CTA tiles               */
 } fd_gemm_desc;
 int fd_gemm(const fd_gemm_desc* d, void* stream);
+
+/* LayerNorm folded into the GEMMs around it (opt-in: FD_LN_FOLD=1 in the Python layer; not part of the default path).
+ * BasicTransformerBlock's norm1 / norm2 / norm3 each feed exactly one Linear (fused QKV, cross-attention Q, GEGLU FF1);
+ * with W' = bf16(W * gamma), colsum[n] = sum_k W'[n,k] and bias' = bias + W beta,
+ *     LayerNorm(x) W^T + bias = rstd_r * (x W'^T) - rstd_r * mean_r * colsum + bias'
+ * so the consumer reads the raw residual stream and applies a per-row affine in its epilogue, and the row statistics come
+ * from the epilogue of the GEMM that produced x (attention-out / FF2 / proj_in): stats_out [M, stats_out_ld] float2 slots
+ * (sum, sum of squares of the bf16-rounded outputs) per (N tile, chunk half); fd_gemm_ln writes the number of slots it used
+ * to stats_out_n, which the consumer passes as stats_in_n.  A call either produces (stats_out) or consumes (stats_in). */
+typedef struct fd_gemm_ln_desc {
+  const void* stats_in;  /* float2 [M, stats_in_ld], or NULL                                             */
+  int64_t stats_in_ld;
+  int32_t stats_in_n;    /* slots per row to sum                                                         */
+  int32_t pad0_;
+  const float* colsum;   /* [N] fp32                                                                     */
+  float inv_c;           /* 1 / (LayerNorm width = K of this GEMM)                                       */
+  float eps;
+  void* stats_out;       /* float2 [M, stats_out_ld], or NULL                                            */
+  int64_t stats_out_ld;  /* >= 2 * ceil(N / block_n); 2 * ceil(N / 32) always suffices                   */
+  int32_t stats_out_n;   /* OUT: slots written per row                                                   */
+  int32_t pad1_;
+} fd_gemm_ln_desc;
+int fd_gemm_ln(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream);
+int32_t fd_sizeof_gemm_ln_desc(void);
 int fd_sizeof_gemm_desc(void);   /* lets a foreign-language binding verify its struct mirror */
 
 /* ---------------------------------------------------------------------------------------------------------
