@@ -39,8 +39,11 @@ def test_producer_statistics_and_folded_consumer(M, C, N, act, mean):
     b = torch.randn(N, device="cuda") * 0.1
     if act == 2:
         w, b = interleave_geglu(w, b)
+    # fp32 truth WITHOUT the bf16 rounding of the LayerNorm output: that rounding belongs to the default path only, and a
+    # reference that contains it is biased towards it (first GPU run: folded 3.7e-3 vs default 1.7e-3 against the rounded
+    # reference for the GEGLU case, where the CPU study against fp64 has the folded form ahead, 2.3e-3 vs 2.9e-3)
     ln = F.layer_norm(h.float(), (C,), gamma, beta, 1e-5)
-    lin = ln.to(BF).float() @ w.float().t() + b
+    lin = ln @ w.float().t() + b
     ref = lin[:, 0::2] * F.gelu(lin[:, 1::2]) if act == 2 else lin
     base = ops.gemm(ops.layernorm(h, gamma, beta), w, bias=b, act=act)      # the default path
     wp, cs, bp = fold_layernorm(w, b, gamma, beta)
