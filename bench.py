@@ -33,6 +33,9 @@ def workload(name):
                          "encoder + tiled VAE, start_point=lr, adain colour fix", lq=(1920, 1080), scale=2, steps=20)
     if name == "1k":
         return dict(name="cfg2: 512x512 -> 1024x1024 2x SR, 20 steps, 1 tile", lq=(512, 512), scale=2, steps=20)
+    if name == "8k":
+        return dict(name="cfg4: 1920x1080 -> 7680x4320 4x SR, 20 steps, 1024-px latent tiles overlap 0.5 (112 tiles), tiled LQ "
+                         "encoder + tiled VAE, start_point=lr, adain colour fix", lq=(1920, 1080), scale=4, steps=20)
     if name == "batch32":
         return dict(name="cfg5: batch of 32 x (512x512 -> 2048x2048 4x SR), 20 steps, 9 tiles per image, images data-parallel "
                          "across ranks (no exchange)", lq=(512, 512), scale=4, steps=20, images=32)

@@ -252,7 +252,7 @@ def test_bench_tile_count_matches_the_tile_walk():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     from faithdiff_dev_b200.tiling import tile_origins
-    for name, want in (("4k", 28), ("1k", 1), ("batch32", 9), ("tiny", 1)):
+    for name, want in (("4k", 28), ("8k", 112), ("1k", 1), ("batch32", 9), ("tiny", 1)):
         wl = bench.workload(name)
         h, w = wl["lq"][1] * wl["scale"] // 8, wl["lq"][0] * wl["scale"] // 8
         assert bench.count_tiles(wl) == len(tile_origins(h, w, 128, 128, 0.5)[0]) == want
