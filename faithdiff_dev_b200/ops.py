@@ -70,10 +70,19 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
         ln.colsum, ln.inv_c, ln.eps = ln_colsum.data_ptr(), 1.0 / a.shape[1], ln_eps
     slots = None
     if stats_out:
-        slots = torch.empty((M, 2 * ((N + 31) // 32), 2), device=a.device, dtype=torch.float32)
+        # slots per row = 2 per N tile; the tile choice is a pure function of the shape, so the count seen on the first call
+        # of a shape sizes the buffer of the later ones (2 * ceil(N / 32) always suffices)
+        key = (M, N, a.shape[1])
+        slots = torch.empty((M, _LN_SLOTS.get(key, 2 * ((N + 31) // 32)), 2), device=a.device, dtype=torch.float32)
         ln.stats_out, ln.stats_out_ld = slots.data_ptr(), slots.shape[1]
     check(lib.fd_gemm_ln(C.byref(d), C.byref(ln), _stream()), "fd_gemm_ln")
-    return (out, RowStats(slots, ln.stats_out_n)) if stats_out else out
+    if stats_out:
+        _LN_SLOTS[key] = ln.stats_out_n
+        return out, RowStats(slots, ln.stats_out_n)
+    return out
+
+
+_LN_SLOTS = {}
 
 
 def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0, alpha=1.0):
