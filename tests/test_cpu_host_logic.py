@@ -277,3 +277,26 @@ def test_bsrnet_host_logic():
     # the tile plan of deg_remove is the reference's (checked bit-exactly through the golden outputs on the GPU); its geometry:
     plan = B.tile_plan(40, 530)
     assert [(p[2], p[3], p[6], p[7]) for p in plan] == [(0, 512, 0, 528), (512, 530, 496, 530)]
+
+
+def test_fold_layernorm_host_preparation():
+    """blocks.fold_layernorm (the host half of FD_LN_FOLD): with W' = bf16(W*gamma), colsum(W') and bias' = bias + W beta, the
+    consumer epilogue's formula rstd*(x W'^T) - rstd*mean*colsum + bias' equals layer_norm(x) W^T + bias (fp32 emulation of the
+    kernel's arithmetic on bf16 inputs, one-pass row sums as the producer epilogue accumulates them)."""
+    from faithdiff_dev_b200.blocks import fold_layernorm, interleave_geglu
+    torch.manual_seed(0)
+    M, Cc, N = 64, 640, 256
+    x = (torch.randn(M, Cc) * 1.7 + 0.8).to(torch.bfloat16)
+    w = (torch.randn(N, Cc) / Cc ** 0.5).to(torch.bfloat16)
+    b = torch.randn(N) * 0.1
+    gamma, beta = 1 + 0.3 * torch.randn(Cc), 0.2 * torch.randn(Cc)
+    for bias, ww in ((b, w), (None, w), interleave_geglu(w, b)[::-1]):
+        wp, cs, bp = fold_layernorm(ww, bias, gamma, beta)
+        assert wp.dtype == torch.bfloat16 and cs.dtype == bp.dtype == torch.float32 and cs.shape == bp.shape == (N,)
+        xf = x.float()
+        s1, s2 = xf.sum(1, keepdim=True), (xf * xf).sum(1, keepdim=True)
+        mean = s1 / Cc
+        rstd = torch.rsqrt((s2 / Cc - mean * mean).clamp_min(0) + 1e-5)
+        out = rstd * (xf @ wp.float().t()) - rstd * mean * cs + bp
+        ref = torch.nn.functional.layer_norm(xf, (Cc,), gamma, beta, 1e-5) @ ww.float().t() + (bias if bias is not None else 0)
+        assert ((out - ref).norm() / ref.norm()).item() < 3e-3
