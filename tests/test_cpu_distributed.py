@@ -79,3 +79,17 @@ def test_shard_images_partitions_the_batch():
         parts = [shard_images(n, r, w) for r in range(w)]
         assert sorted(i for p in parts for i in p) == list(range(n))
         assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+def test_unit_shards_and_launch_groups_for_every_world_size():
+    """(tile, CFG-branch) units of the 4K (28 tiles) and 8K (112 tiles) layouts over 1, 2, 4, 8 ranks: contiguous balanced ranges
+    that cover every unit once, and launch groups that keep the order and the per-launch sample cap."""
+    from faithdiff_dev_b200.dist import plan_unit_groups, shard_units
+    for T in (28, 112, 9, 1):
+        for W in (1, 2, 4, 8):
+            shards = [shard_units(T, r, W) for r in range(W)]
+            assert [u for s in shards for u in s] == list(range(2 * T))
+            assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+            for s in shards:
+                groups = plan_unit_groups(s, max_samples=16)
+                assert [u for g in groups for u in g] == s and all(1 <= len(g) <= 16 for g in groups)
