@@ -44,6 +44,7 @@ lib.fd_last_error.restype = C.c_char_p
 lib.fd_launch_count.restype = C.c_int64
 lib.fd_groupnorm_work_floats.restype = C.c_int64
 lib.fd_groupnorm_sync_bytes.restype = C.c_int64
+lib.fd_peer_region_bytes.restype = C.c_int64
 lib.fd_colorfix_work_floats.restype = C.c_int64
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
@@ -74,6 +75,13 @@ _SIGS = {
     "fd_unit_accumulate": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
     "fd_scale_div": [vp, vp, i32, f32, i64, vp],
+    "fd_peer_region_bytes": [i64],
+    "fd_peer_alloc": [C.POINTER(vp), i64],
+    "fd_peer_free": [vp],
+    "fd_peer_ipc_handle": [vp, vp],
+    "fd_peer_ipc_open": [vp, C.POINTER(vp)],
+    "fd_peer_ipc_close": [vp],
+    "fd_canvas_exchange_finalize": [C.POINTER(vp), i32, i32, i32, C.c_uint32, i64, vp, vp, vp, i32, vp],
     "fd_seam_blend": [vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, vp],
     "fd_image_preprocess": [vp, vp, vp, i32, i32, vp],
     "fd_image_postprocess": [vp, i32, vp, i32, i32, vp],

@@ -89,3 +89,66 @@ def exchange_canvas(numerator, group=None):
     if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size(group) > 1:
         torch.distributed.all_reduce(numerator, op=torch.distributed.ReduceOp.SUM, group=group)
     return numerator
+
+
+class PeerCanvas:
+    """Opt-in (FD_P2P_EXCHANGE=1; not yet run on a multi-GPU box): the per-step exchange as ONE kernel over NVLink peer memory
+    instead of an NCCL all-reduce + fd_canvas_finalize (csrc/peer_exchange.cu).  Every rank's fp32 numerator canvas lives in a
+    cudaMalloc'd region that all ranks of the node map through CUDA IPC; `numerator(step)` is the slot this rank accumulates
+    step `step` into, `exchange_finalize(step, count, dtype)` publishes it, waits for the peers, sums all canvases in rank
+    order and divides by the count map.  torch.distributed only carries the 64-byte IPC handles, once."""
+
+    def __init__(self, shape, rank, world_size, group=None, device=None):
+        import ctypes as C
+        from ._lib import check, lib
+        self.shape, self.rank, self.world = tuple(shape), rank, world_size
+        self.n = 1
+        for d in self.shape:
+            self.n *= d
+        assert self.n % 4 == 0, "canvas size must be a multiple of 4 floats"
+        self.n_pad = (self.n + 63) // 64 * 64
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self._lib, self._check, self._C = lib, check, C
+        mine = C.c_void_p()
+        check(lib.fd_peer_alloc(C.byref(mine), lib.fd_peer_region_bytes(self.n)), "fd_peer_alloc")
+        self._mine = mine.value
+        handle = C.create_string_buffer(64)
+        check(lib.fd_peer_ipc_handle(C.c_void_p(self._mine), handle), "fd_peer_ipc_handle")
+        handles = [None] * world_size
+        torch.distributed.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._opened, ptrs = [], []
+        for r in range(world_size):
+            if r == rank:
+                ptrs.append(self._mine)
+            else:
+                q = C.c_void_p()
+                check(lib.fd_peer_ipc_open(C.create_string_buffer(handles[r], 64), C.byref(q)), "fd_peer_ipc_open")
+                self._opened.append(q.value)
+                ptrs.append(q.value)
+        self._regions = (C.c_void_p * world_size)(*ptrs)
+        torch.distributed.barrier(group=group)          # nobody signals before everyone has mapped everyone
+
+    def numerator(self, step):
+        """fp32 view [shape] of this rank's canvas slot for scheduler step `step` (1-based counter); zero it before accumulating."""
+        iface = {"shape": self.shape, "typestr": "<f4", "version": 2,
+                 "data": (self._mine + (step & 1) * self.n_pad * 4, False)}
+        holder = type("_PeerSlot", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device=self.device)
+
+    def exchange_finalize(self, step, count, lowp_dtype):
+        from .ops import _DT, _p, _stream
+        out = torch.empty(self.shape, device=self.device, dtype=torch.float32)
+        lowp = torch.empty(self.shape, device=self.device, dtype=lowp_dtype)
+        self._check(self._lib.fd_canvas_exchange_finalize(self._regions, self.rank, self.world, step & 1, step, self.n, _p(count),
+                                                          _p(out), _p(lowp), _DT[lowp_dtype], _stream()), "fd_canvas_exchange_finalize")
+        return out, lowp
+
+    def close(self):
+        C = self._C
+        torch.cuda.synchronize()
+        for q in self._opened:
+            self._lib.fd_peer_ipc_close(C.c_void_p(q))
+        self._opened = []
+        if self._mine:
+            self._lib.fd_peer_free(C.c_void_p(self._mine))
+            self._mine = None

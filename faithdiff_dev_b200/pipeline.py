@@ -3,6 +3,7 @@ same constructor components and `__call__` signature, same tile layout / blend /
 re-organised for the hardware (step-invariant work hoisted, CFG-identical stem evaluated once, per-step host logic
 reduced to three scalars, the whole per-step tail fused into one kernel, tiles sharded over ranks with one NCCL
 all-reduce of the fp32 overlap accumulation per scheduler step)."""
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Union
 
@@ -383,6 +384,15 @@ class FaithDiffStableDiffusionXLPipeline:
         n_local = len(my_units)
         eps = torch.empty((n_local,) + tuple(tiles.shape[1:]), device=dev, dtype=dt)     # unit order (pairs when 1 GPU)
         canvas_lowp = None
+        peer = None
+        if self.world_size > 1 and os.environ.get("FD_P2P_EXCHANGE", "0") == "1":
+            key = (tuple(shape), self.rank, self.world_size)
+            if getattr(self, "_peer_key", None) != key:
+                if getattr(self, "_peer", None) is not None:
+                    self._peer.close()
+                from .dist import PeerCanvas
+                self._peer, self._peer_key, self._peer_step = PeerCanvas(shape, self.rank, self.world_size, self.process_group, dev), key, 0
+            peer = self._peer
         for i in range(len(ts)):
             sigma, sigma_next, _ = sch.step_scalars(i)
             next_div = sch.step_scalars(i + 1)[2] if i + 1 < len(ts) else 1.0
@@ -394,6 +404,15 @@ class FaithDiffStableDiffusionXLPipeline:
             if self.world_size == 1:
                 canvas, canvas_lowp, tiles, scaled = ops.cfg_euler_blend(eps.view((T, 2) + tuple(tiles.shape[1:])), tiles, weights,
                                                                          origins, h, w, guidance_scale, sigma, sigma_next, next_div)
+            elif peer is not None:
+                # opt-in: exchange + divide as one kernel over NVLink peer memory (dist.PeerCanvas, csrc/peer_exchange.cu)
+                self._peer_step += 1
+                num = peer.numerator(self._peer_step)
+                num.zero_()
+                ops.unit_accumulate(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
+                canvas, canvas_lowp = peer.exchange_finalize(self._peer_step, count, dt)
+                tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)
+                scaled = ops.scale_div(tiles, next_div)
             else:
                 num = torch.zeros(shape, device=dev, dtype=torch.float32)
                 ops.unit_accumulate(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)

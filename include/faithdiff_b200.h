@@ -197,6 +197,20 @@ int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype
                        int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
 int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
                        int32_t lowp_dtype, int64_t n, void* stream);
+/* The same exchange as ONE kernel over NVLink peer memory (opt-in, FD_P2P_EXCHANGE=1; peer_exchange.cu): every rank's numerator
+ * canvas lives in a region all peers have mapped through CUDA IPC ([canvas parity 0][canvas parity 1][flags],
+ * fd_peer_region_bytes(n)); the kernel publishes this rank's step flag to all peers, waits for theirs, sums the canvases in rank
+ * order with P2P loads and divides by the count map — the all-reduce and fd_canvas_finalize in one launch, deterministic and
+ * identical on all ranks.  regions: host array of `world` device pointers (own region + IPC-opened peers) in rank order;
+ * step: a counter != 0 that increases by one per scheduler step; parity = step & 1 selects the canvas slot.               */
+int64_t fd_peer_region_bytes(int64_t n_floats);
+int fd_peer_alloc(void** ptr, int64_t bytes);
+int fd_peer_free(void* ptr);
+int fd_peer_ipc_handle(void* ptr, void* handle64);
+int fd_peer_ipc_open(const void* handle64, void** ptr);
+int fd_peer_ipc_close(void* ptr);
+int fd_canvas_exchange_finalize(const void* const* regions, int32_t rank, int32_t world, int32_t parity, uint32_t step, int64_t n,
+                                const float* count, float* canvas_f32, void* canvas_lowp, int32_t lowp_dtype, void* stream);
 /* EulerDiscreteScheduler.scale_model_input (pipeline…:1336): out = x / sqrt(sigma^2+1), rounded to dtype         */
 int fd_scale_div(const void* x, void* out, int32_t dtype, float div, int64_t n, void* stream);
 /* VAE / LQ-encoder seam blend (Encoder.blend_v/blend_h, …extension.py:150-162): in-place linear cross-fade of

@@ -1,6 +1,8 @@
 #!/bin/bash
 # First GPU call of the next round (gpurun --timeout 900 -- bash scripts/gpu_experimental.sh): acceptance tests and A/B numbers of
 # the opt-in paths written at the end of round 1 — LayerNorm folding (FD_LN_FOLD=1), 8-softmax-warp attention (FD_ATTN_W8=1).
+# The peer-memory exchange (FD_P2P_EXCHANGE=1) needs 2 GPUs:
+#   gpurun --gpus 2 --timeout 400 -- 'FD_TEST_EXPERIMENTAL=1 timeout 350 python -m pytest tests/test_gpu_multi.py -q'
 # Every step runs under its own `timeout`: a protocol error in a new kernel is a hang, not a wrong number.
 mkdir -p gpurun_out
 FD_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_gpu_ln_fold.py tests/test_gpu_attention_variants.py -q > gpurun_out/exp_tests.log 2>&1; echo "experimental tests rc=$?"

@@ -20,3 +20,17 @@ def test_two_rank_pipeline_matches_single_rank():
                        timeout=800, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "PSNR(N-rank vs 1-rank)" in r.stdout
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.skipif(os.environ.get("FD_TEST_EXPERIMENTAL") != "1", reason="opt-in path; set FD_TEST_EXPERIMENTAL=1")
+def test_two_rank_pipeline_with_peer_memory_exchange():
+    """Same check with FD_P2P_EXCHANGE=1: the per-step exchange as one kernel over NVLink peer memory (dist.PeerCanvas,
+    csrc/peer_exchange.cu) instead of the NCCL all-reduce.  EXPERIMENTAL: not yet run on a multi-GPU box; run under `timeout`."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29534", os.path.join(ROOT, "scripts", "dev_multigpu_check.py")], capture_output=True, text=True,
+                       timeout=300, cwd=ROOT, env=dict(os.environ, FD_P2P_EXCHANGE="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "PSNR(N-rank vs 1-rank)" in r.stdout
