@@ -53,6 +53,7 @@ _SIGS = {
     "fd_gemm_ln": [C.POINTER(GemmDesc), C.POINTER(GemmLnDesc), vp],
     "fd_attention_d64": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
     "fd_attention_d64_causal": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, f32, vp],
+    "fd_attention_d512": [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, f32, vp],
     "fd_softmax_rows": [vp, i64, vp, i64, i64, i64, f32, vp],
     "fd_groupnorm_work_floats": [i32, i32, i32],
     "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
@@ -74,6 +75,8 @@ _SIGS = {
     "fd_tile_accumulate": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
     "fd_unit_accumulate": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
+    "fd_unit_numerator": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "fd_canvas_finalize_retile": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp],
     "fd_scale_div": [vp, vp, i32, f32, i64, vp],
     "fd_peer_region_bytes": [i64],
     "fd_peer_alloc": [C.POINTER(vp), i64],

@@ -84,8 +84,10 @@ class ResnetBlock:
 
 
 class VaeAttention:
-    """diffusers Attention in the VAE mid block: GroupNorm, 1 head with d = C (512), q/k/v/out with bias, residual.
-    d=512 does not fit the d64 flash kernel: scores and P·V run as tensor-core GEMMs around a row-softmax kernel."""
+    """diffusers Attention in the VAE / LQ-encoder mid block (unet_2d_condition_vae_extension.py:96-106): GroupNorm, 1 head with
+    d = C, q/k/v/out with bias, residual.  C = 512 (the real networks): one fused QKV GEMM over all samples, the flash-style
+    fd_attention_d512 kernel (no [L, L] matrix in HBM, no per-sample Python loop), out-projection + residual in the GEMM epilogue.
+    Other widths (the tests' small configurations): scores and P·V as tensor-core GEMMs around a row-softmax kernel."""
 
     def __init__(self, W, groups, eps):
         self.groups, self.eps = groups, eps
@@ -94,11 +96,17 @@ class VaeAttention:
         self.wk, self.bk = W.mat("to_k.weight"), W.f32("to_k.bias")
         self.wv, self.bv = W.mat("to_v.weight"), W.f32("to_v.bias")
         self.wo, self.bo = W.mat("to_out.0.weight"), W.f32("to_out.0.bias")
+        self.wqkv = torch.cat([self.wq, self.wk, self.wv], 0).contiguous()
+        self.bqkv = torch.cat([self.bq, self.bk, self.bv], 0).contiguous()
 
     def __call__(self, x):
         B, H, Wd, Cc = x.shape
         L = H * Wd
         n = ops.groupnorm(x, self.ng, self.nb, self.groups, self.eps, False)
+        if Cc == 512 and os.environ.get("FD_VAE_ATTN_GEMM", "0") != "1":
+            qkv = ops.gemm(n.reshape(B * L, Cc), self.wqkv, bias=self.bqkv)
+            a = ops.attention_d512(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, L, Cc ** -0.5)
+            return ops.gemm(a, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc)).view(B, H, Wd, Cc)
         out = torch.empty_like(x)
         Lp = (L + 7) // 8 * 8            # token count padded to the 16-byte vector width of the GEMM epilogue
         for b in range(B):
@@ -144,9 +152,10 @@ def interleave_geglu(w, b):
     return wi, bi
 
 
-# FD_LN_FOLD=1 (opt-in, not the default path): the three LayerNorms of a transformer block are folded into the GEMMs around
-# them (fd_gemm_ln): no LayerNorm launch, no normalised copy of the residual stream
-LN_FOLD = os.environ.get("FD_LN_FOLD", "0") == "1"
+# The three LayerNorms of a transformer block are folded into the GEMMs around them (fd_gemm_ln): no LayerNorm launch, no
+# normalised copy of the residual stream.  Default since round 2 (GPU-validated: kernel, stack and full-UNet
+# parity; 4K restoration 8806 -> 8750 ms); FD_LN_FOLD=0 restores the LayerNorm launches for A/B runs.
+LN_FOLD = os.environ.get("FD_LN_FOLD", "1") == "1"
 
 
 def fold_layernorm(w, bias, gamma, beta):
@@ -174,10 +183,12 @@ class TransformerBlock:
         self.wff2, self.bff2 = W.mat("ff.net.2.weight"), W.f32("ff.net.2.bias")
         self.C = self.wo1.shape[0]
         self.scale = (self.C // heads) ** -0.5
-        if LN_FOLD:
+        self.fold = LN_FOLD
+        if self.fold:
             self.f_qkv = fold_layernorm(self.wqkv, None, *self.ln[0])
             self.f_q2 = fold_layernorm(self.wq2, None, *self.ln[1])
             self.f_ff1 = fold_layernorm(self.wff1, self.bff1, *self.ln[2])
+            self.wqkv = self.wq2 = self.wff1 = self.bff1 = None      # only the folded copies stay resident
 
     def text_kv(self, text2d):
         return ops.gemm(text2d, self.wkv2)
@@ -230,7 +241,7 @@ class Transformer2D:
         B, H, Wd, Cc = x.shape
         L = H * Wd
         n = ops.groupnorm(x, self.ng, self.nb, self.groups, 1e-6, False)
-        if LN_FOLD:
+        if self.blocks and self.blocks[0].fold:
             h, st = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi, stats_out=True)
             for blk, kv in zip(self.blocks, kv_list):
                 h, st = blk.call_folded(h, st, B, L, kv, lk)

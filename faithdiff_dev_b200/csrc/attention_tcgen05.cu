@@ -57,34 +57,9 @@ __device__ __forceinline__ void exp2_pair_poly(float a0, float a1, float& e0, fl
   e1 = __int_as_float(__float_as_int(t1) * 8388608 + __float_as_int(q1));
 }
 
-// one-column TMEM store / load (a value per lane) and a named barrier: the two warps that share a TMEM lane quadrant in the
-// 8-softmax-warp variant exchange their row maxima / row sums through two spare accumulator columns
-__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t v;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-  return v;
-}
-// 64-thread named barrier 1 + quad with a literal id (a register id makes ptxas reserve all 16 barriers of the CTA)
-__device__ __forceinline__ void quad_pair_sync(int quad) {
-  switch (quad) {
-    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-  }
-}
-
 // kPolyOf8: of every 8 consecutive pairs of a row, the first kPolyOf8 use exp2_pair_poly, the rest MUFU ex2 (0 = all MUFU)
-// kW8 (opt-in, FD_ATTN_W8=1, not yet run on a GPU): EIGHT softmax warps, two per TMEM lane quadrant, each thread owning 64 of
-// its row's 128 keys of a block.  The 4-warp kernel keeps two softmax warps per scheduler (2 CTAs x 4 warps / 4 SMSPs), each a
-// single dependent instruction stream: MUFU is 62 % busy and the tensor pipe 31 %, the rest is latency nobody covers.  Twice
-// the warps at half the registers (<= 102) double what each scheduler can pick from.  The two threads of a row agree on the
-// row maximum and the final row sum through spare TMEM columns (192..197) and a 64-thread named barrier per quadrant.
-template <int kPolyOf8, int kW8 = 0>
-__global__ void __launch_bounds__(kW8 ? 320 : 192, 2) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+template <int kPolyOf8>
+__global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;            // 2 stages
@@ -103,8 +78,8 @@ __global__ void __launch_bounds__(kW8 ? 320 : 192, 2) attention_d64_kernel(const
       mbar_init(&bars->v_full[s], 1); mbar_init(&bars->v_empty[s], 1);
     }
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->s_read, kW8 ? 8 : 4);
-    mbar_init(&bars->p_full, kW8 ? 8 : 4);
+    mbar_init(&bars->s_read, 4);
+    mbar_init(&bars->p_full, 4);
     mbar_init(&bars->o_done, 1);
     fence_barrier_init();
   }
@@ -182,144 +157,6 @@ __global__ void __launch_bounds__(kW8 ? 320 : 192, 2) attention_d64_kernel(const
         tc_commit(&bars->o_done);
       }
     }
-  } else if constexpr (kW8 != 0) {
-    // ---------------------------------------------------------------- softmax, 8 warps: thread = (row, half of the keys)
-    const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int r = quad * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(quad * 32) << 16);
-    float m_used = -INFINITY, l = 0.f;
-    uint8_t* prow = sP + half * kTile + r * 128;          // this thread's 64 keys are P half-tile `half`
-    const int sw = r & 7;
-    const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
-    auto exchange = [&](uint32_t col, float mine) -> float {   // value of the other half's thread of this row
-      tmem_st1(t_lane + col + half, __float_as_uint(mine));
-      tmem_st_wait();
-      tc_fence_before();
-      quad_pair_sync(quad);
-      tc_fence_after();
-      const uint32_t o = tmem_ld1(t_lane + col + (half ^ 1));
-      tmem_ld_wait();
-      return __uint_as_float(o);
-    };
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&bars->s_full, j & 1);
-      tc_fence_after();
-      uint32_t v[64];
-      tmem_ld32(t_lane + half * 64, reinterpret_cast<uint32_t(&)[32]>(v[0]));
-      tmem_ld32(t_lane + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(v[32]));
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->s_read);
-      const int kv0 = j * kKV + half * 64;
-      const bool full = j * kKV + kKV <= p.lk;
-      float mx = m_used;
-      if (full) {
-        float m1 = mx, m2 = mx, m3 = mx;
-#pragma unroll
-        for (int i = 0; i < 64; i += 8) {
-          mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-          m1 = max3_f(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-          m2 = max3_f(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-          m3 = max3_f(m3, __uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-        }
-        mx = fmaxf(max3_f(mx, m1, m2), m3);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 64; ++i)
-          if (kv0 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
-      }
-      mx = fmaxf(mx, exchange(192 + 2 * (j & 1), mx));      // both threads of the row now hold the same maximum
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        mbar_wait(&bars->o_done, (j - 1) & 1);
-        tc_fence_after();
-        const bool grew = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grew)) {                  // same rows, same values in both warps of the quadrant
-          const float alpha = fast_exp2((m_used - mx) * p.scale_log2);
-#pragma unroll 1
-          for (int q = 0; q < 2; ++q) {                       // this thread rescales its 32 of the 64 output columns
-            uint32_t o[16];
-            tmem_ld16(t_lane + 128 + half * 32 + q * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(t_lane + 128 + half * 32 + q * 16, o);
-          }
-          tmem_st_wait();
-          l *= alpha;
-          m_used = mx;
-        }
-      }
-      const float nmxs = -m_used * p.scale_log2;
-      const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
-      uint64_t lsum2 = 0ull;
-      auto exp_block = [&](auto full_tag) {
-        constexpr bool kFull = decltype(full_tag)::value;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), scale2, nmxs2);
-            float a0, a1;
-            unpack_f2(t, a0, a1);
-            if constexpr (kPolyOf8 > 0) {
-              if (((i >> 1) & 7) < kPolyOf8) {
-                exp2_pair_poly(a0, a1, a0, a1);
-              } else {
-                a0 = fast_exp2(a0);
-                a1 = fast_exp2(a1);
-              }
-            } else {
-              a0 = fast_exp2(a0);
-              a1 = fast_exp2(a1);
-            }
-            if constexpr (!kFull) {
-              if (kv0 + c * 32 + i >= p.lk) a0 = 0.f;
-              if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
-            }
-            lsum2 = add_f2(lsum2, pack_f2(a0, a1));
-            pk[i >> 1] = pack_bf16(a0, a1);
-          }
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = c * 4 + g;
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-          }
-        }
-      };
-      if (full) exp_block(std::true_type{}); else exp_block(std::false_type{});
-      float ls0, ls1;
-      unpack_f2(lsum2, ls0, ls1);
-      l += ls0 + ls1;
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full);
-    }
-    mbar_wait(&bars->o_done, (nkv - 1) & 1);
-    tc_fence_after();
-    const float inv = 1.f / (l + exchange(196, l));
-    const int qi = qblk * kQ + r;
-    __nv_bfloat16* dst = p.out + ((long long)b * p.lq + qi) * p.ldo + head * kD + half * 32;
-    uint32_t o[32];
-    tmem_ld32(t_lane + 128 + half * 32, o);
-    tmem_ld_wait();
-    if (qi < p.lq) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o[g * 8 + 0]) * inv, __uint_as_float(o[g * 8 + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o[g * 8 + 2]) * inv, __uint_as_float(o[g * 8 + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o[g * 8 + 4]) * inv, __uint_as_float(o[g * 8 + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o[g * 8 + 6]) * inv, __uint_as_float(o[g * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(dst + g * 8) = u;
-      }
-    }
-    tc_fence_before();
   } else {
     const int quad = warp & 3;
     const int r = quad * 32 + lane;                       // query row within the block
@@ -715,8 +552,6 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<0, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_shortkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_short));
     attr = true;
   }
@@ -738,14 +573,10 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
     FD_CHECK_CUDA(launch_pdl(attention_d64_shortkv_kernel, grid, dim3(192), smem_short, stream, 1, p));
   } else {
     dim3 grid(nqb, heads, batch);
-    // FD_ATTN_POLY = 2 / 3 / 4: that many of every 8 exponential pairs on the FMA pipe (opt-in; not yet measured on a GPU)
+    // FD_ATTN_POLY = 2 / 3 / 4: that many of every 8 exponential pairs on the FMA pipe (opt-in; measured: 3 gives +2 % at 4096 keys)
     static int poly = -1;
     if (poly < 0) { const char* e = getenv("FD_ATTN_POLY"); poly = e ? atoi(e) : 0; }
-    static int w8 = -1;
-    if (w8 < 0) { const char* e = getenv("FD_ATTN_W8"); w8 = e ? atoi(e) : 0; }     // opt-in: 8 softmax warps (not yet run on a GPU)
-    if (w8 && poly == 3) FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<3, 1>), grid, dim3(320), smem_bytes, stream, 1, p));
-    else if (w8) FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<0, 1>), grid, dim3(320), smem_bytes, stream, 1, p));
-    else if (poly == 2) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<2>, grid, dim3(192), smem_bytes, stream, 1, p));
+    if (poly == 2) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<2>, grid, dim3(192), smem_bytes, stream, 1, p));
     else if (poly == 3) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<3>, grid, dim3(192), smem_bytes, stream, 1, p));
     else if (poly == 4) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<4>, grid, dim3(192), smem_bytes, stream, 1, p));
     else FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<0>, grid, dim3(192), smem_bytes, stream, 1, p));

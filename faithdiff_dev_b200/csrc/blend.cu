@@ -125,14 +125,14 @@ __global__ void unit_accumulate_kernel(const void* __restrict__ x_tiles, const v
                                        const double* __restrict__ weights, const int* __restrict__ org,
                                        const int* __restrict__ unit_tile, const float* __restrict__ unit_coef,
                                        const int* __restrict__ unit_addx, int nunits, int c, int h, int w, int k1, int k2,
-                                       float* __restrict__ canvas_num) {
+                                       float* __restrict__ canvas_num, int overwrite) {
   const long long total = (long long)c * h * w;
   const long long plane = (long long)k1 * k2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = (int)(i % w);
     const int y = (int)((i / w) % h);
     const int ch = (int)(i / ((long long)w * h));
-    double acc = (double)canvas_num[i];
+    double acc = overwrite ? 0.0 : (double)canvas_num[i];
     for (int u = 0; u < nunits; ++u) {
       const int t = unit_tile[u];
       const int ly = y - org[2 * t], lx = x - org[2 * t + 1];
@@ -152,6 +152,32 @@ __global__ void canvas_finalize_kernel(const float* __restrict__ num, const floa
     const float r = __fdiv_rn(num[i], count[i]);
     if (out) out[i] = r;
     if (lowp) store_lowp(lowp, lowp_dtype, i, r);
+  }
+}
+
+// multi-GPU step tail after the exchange, one launch: divide by the count map, cast, re-tile (LocalAttention.grids of the next
+// step) and scale_model_input — the gather-form tail of tile_blend_kernel on an already summed numerator
+__global__ void canvas_finalize_retile_kernel(const float* __restrict__ num, const float* __restrict__ count, float* __restrict__ out,
+                                              void* lowp, int dtype, const int* __restrict__ org, int ntiles, int c, int h, int w,
+                                              int k1, int k2, float inv_next_div, void* next_tiles, void* next_scaled) {
+  const long long total = (long long)c * h * w;
+  const long long plane = (long long)k1 * k2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w);
+    const int y = (int)((i / w) % h);
+    const int ch = (int)(i / ((long long)w * h));
+    const float r = __fdiv_rn(num[i], count[i]);
+    if (out) out[i] = r;
+    if (lowp) store_lowp(lowp, dtype, i, r);
+    const float rl = round_lowp(r, dtype);
+    const float rs = round_lowp(__fmul_rn(rl, inv_next_div), dtype);
+    for (int t = 0; t < ntiles; ++t) {
+      const int ly = y - org[2 * t], lx = x - org[2 * t + 1];
+      if (ly < 0 || ly >= k1 || lx < 0 || lx >= k2) continue;
+      const long long o = ((long long)t * c + ch) * plane + (long long)ly * k2 + lx;
+      store_lowp(next_tiles, dtype, o, rl);
+      store_lowp(next_scaled, dtype, o, rs);
+    }
   }
 }
 
@@ -281,7 +307,34 @@ extern "C" int fd_unit_accumulate(const void* x_tiles, const void* eps_units, in
   FD_REQUIRE(x_tiles && eps_units && weights && origins_ij && unit_tile && unit_coef && unit_addx && canvas_num,
              "fd_unit_accumulate: null pointer");
   unit_accumulate_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
-      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num);
+      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 0);
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_unit_numerator(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+                                 const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef,
+                                 const int32_t* unit_addx, int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1,
+                                 int32_t k2, float* canvas_num, void* stream_) {
+  FD_REQUIRE(x_tiles && eps_units && weights && origins_ij && unit_tile && unit_coef && unit_addx && canvas_num,
+             "fd_unit_numerator: null pointer");
+  unit_accumulate_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
+      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 1);
+  ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_canvas_finalize_retile(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
+                                         int32_t dtype, const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w,
+                                         int32_t k1, int32_t k2, float next_scale_div, void* next_tiles, void* next_scaled,
+                                         void* stream_) {
+  FD_REQUIRE(canvas_num && count && origins_ij && next_tiles && next_scaled && dtype >= 0 && dtype <= 2,
+             "fd_canvas_finalize_retile: bad arguments");
+  canvas_finalize_retile_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
+      canvas_num, count, canvas_f32, canvas_lowp, dtype, origins_ij, ntiles, c, h, w, k1, k2, 1.0f / next_scale_div, next_tiles,
+      next_scaled);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

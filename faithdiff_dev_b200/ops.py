@@ -131,6 +131,16 @@ def attention(q, k, v, batch, heads, lq, lk, scale, out=None, causal=False):
     return out
 
 
+def attention_d512(q, k, v, batch, l, scale, out=None):
+    """Single head, head_dim 512 (VAE / LQ-encoder mid block): q, k, v bf16 row views [batch*l, 512] -> out [batch*l, 512]."""
+    assert q.shape[1] == 512 and k.shape[1] == 512 and v.shape[1] == 512 and q.shape[0] == batch * l
+    if out is None:
+        out = torch.empty((batch * l, 512), device=q.device, dtype=BF16)
+    check(lib.fd_attention_d512(_p(q), q.stride(0), _p(k), k.stride(0), _p(v), v.stride(0), _p(out), out.stride(0), batch, l,
+                                scale, _stream()), "fd_attention_d512")
+    return out
+
+
 def softmax_rows(s, alpha=1.0, cols=None):
     """Row softmax over the first `cols` columns (default all); remaining columns of p are zero."""
     cols = cols or s.shape[1]
@@ -332,6 +342,27 @@ def unit_accumulate(x_tiles, eps_units, weights, origins, unit_tile, unit_coef, 
     _, _, h, w = canvas_num.shape
     check(lib.fd_unit_accumulate(_p(x_tiles), _p(eps_units), _DT[x_tiles.dtype], _p(weights), _p(origins), _p(unit_tile), _p(unit_coef),
                                  _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()), "fd_unit_accumulate")
+
+
+def unit_numerator(x_tiles, eps_units, weights, origins, unit_tile, unit_coef, unit_addx, canvas_num):
+    """canvas_num := this rank's blend numerator (overwrites; no zero-fill needed)."""
+    U, c, k1, k2 = eps_units.shape
+    _, _, h, w = canvas_num.shape
+    check(lib.fd_unit_numerator(_p(x_tiles), _p(eps_units), _DT[x_tiles.dtype], _p(weights), _p(origins), _p(unit_tile), _p(unit_coef),
+                                _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()), "fd_unit_numerator")
+
+
+def canvas_finalize_retile(num, count, origins, k1, k2, next_div, lowp_dtype):
+    """(canvas fp32, canvas lowp, next tiles, next scaled tiles) from the exchanged numerator: one launch."""
+    _, c, h, w = num.shape
+    T = origins.shape[0]
+    out = torch.empty_like(num)
+    lowp = torch.empty(num.shape, device=num.device, dtype=lowp_dtype)
+    nxt = torch.empty((T, c, k1, k2), device=num.device, dtype=lowp_dtype)
+    nxs = torch.empty_like(nxt)
+    check(lib.fd_canvas_finalize_retile(_p(num), _p(count), _p(out), _p(lowp), _DT[lowp_dtype], _p(origins), T, c, h, w, k1, k2,
+                                        next_div, _p(nxt), _p(nxs), _stream()), "fd_canvas_finalize_retile")
+    return out, lowp, nxt, nxs
 
 
 def canvas_finalize(num, count, lowp_dtype):

@@ -43,7 +43,11 @@ class TileStepGraph:
         self.paired = self.slot_of_sample == tuple(i // 2 for i in range(self.ns)) and self.ns % 2 == 0
         self.gather_idx = torch.tensor(self.slot_of_sample, device=dev, dtype=torch.long)
         self.scaled = torch.zeros((self.nt, unet.config.in_channels, k1, k2), device=dev, dtype=lowp)
-        self.cond = torch.zeros((self.nt, k1, k2, c0), device=dev, dtype=BF16)
+        # stem input [conv_in(sample) | condition embedding]: the cached, step-invariant embedding of the group's tiles is
+        # written straight into its channel half (one strided copy per replay; launch groups share a graph, so it cannot be
+        # baked in), conv_in writes the other half inside the graph
+        self.cat = torch.zeros((self.nt, k1, k2, 2 * c0), device=dev, dtype=BF16)
+        self.c0 = c0
         self.temb = torch.zeros((self.ns, unet.temb_w.shape[0]), device=dev, dtype=torch.float32)
         # static text K/V per sample (the attention kernel indexes K/V rows by sample); a new prompt is copied in with
         # set_text_kv() — no re-capture
@@ -71,19 +75,18 @@ class TileStepGraph:
 
     def _run(self):
         u = self.unet
-        x1 = u.stem(self.scaled, self.cond, add_sample=self.add_sample, groups=self.nt)        # [nt,h,w,c0]
+        x1 = u.stem(self.scaled, None, add_sample=self.add_sample, groups=self.nt, cat=self.cat)  # [nt,h,w,c0]
         if self.paired:
             x2 = x1.unsqueeze(1).expand(-1, 2, -1, -1, -1).reshape((self.ns,) + tuple(x1.shape[1:])).contiguous()
         else:
             x2 = x1.index_select(0, self.gather_idx)
         self.eps = u.trunk(x2, self.temb, self.kv, self.lk, self.scaled.dtype)                  # [ns,4,k1,k2]
 
-    def __call__(self, scaled_tiles, cond_list, temb_rows, eps_out):
-        """scaled_tiles: list of [4,k1,k2] (one per tile slot); cond_list: per-slot [1,k1,k2,c0]; temb_rows [ns, ΣC];
+    def __call__(self, scaled_tiles, cond_tiles, temb_rows, eps_out):
+        """scaled_tiles [nt,4,k1,k2] and cond_tiles [nt,k1,k2,c0] (the group's tile slots, in slot order); temb_rows [ns, ΣC];
         eps_out [ns,4,k1,k2] destination view."""
-        for i, (sc, cd) in enumerate(zip(scaled_tiles, cond_list)):
-            self.scaled[i].copy_(sc)
-            self.cond[i].copy_(cd[0])
+        self.scaled.copy_(scaled_tiles)
+        self.cat[..., self.c0:].copy_(cond_tiles)
         self.temb.copy_(temb_rows)
         if self.graph is not None:
             self.graph.replay()
@@ -108,6 +111,7 @@ class FaithDiffStableDiffusionXLPipeline:
         self.watermark = None
         self.device = torch.device("cuda")
         self.rank, self.world_size, self.process_group = 0, 1, None
+        self._dist = None
         self.tiles_per_launch = 8          # upper bound; the launch plan mixes group sizes 1..N by measured cost
         self.use_cuda_graph = True
         self._graphs = {}
@@ -141,10 +145,14 @@ class FaithDiffStableDiffusionXLPipeline:
         self.denoise_encoder.disable_tiling()
 
     def set_distributed(self, rank, world_size, process_group=None):
-        """Multi-GPU: tiles are sharded round-robin over ranks; one all-reduce of the fp32 canvas per step."""
+        """Multi-GPU: (tile, CFG-branch) units in contiguous balanced ranges per rank, one exchange of the fp32 canvas per
+        scheduler step; the tiled LQ-encoder / VAE stages shard their tiles by area.  The context lives on THIS pipeline (it is
+        handed to the encoder / VAE per call), so pipelines of one process do not share it.
+        RNG contract: the initial latents (and, with start_point='lr', the posterior sample and the DDPM noise) are drawn on
+        every rank and then REPLACED by rank 0's values (one broadcast per image), so ranks may be seeded differently."""
         self.rank, self.world_size, self.process_group = rank, world_size, process_group
-        from . import vae as _vae
-        _vae.DIST.update(rank=rank, world=world_size, group=process_group)
+        from .vae import DistCtx
+        self._dist = DistCtx(rank, world_size, process_group) if world_size > 1 else None
 
     def check_inputs(self, lr_img, prompt, height, width, prompt_embeds, negative_prompt, negative_prompt_embeds,
                      pooled_prompt_embeds, negative_pooled_prompt_embeds):
@@ -273,7 +281,7 @@ class FaithDiffStableDiffusionXLPipeline:
         """prepare_image_latents (pipeline…:950-1004) → denoise_encoder (LQ features), NHWC bf16 [1,h,w,512]."""
         enc = self.denoise_encoder
         x_nchw = ops.nhwc_to_nchw(lr_nhwc, BF16)
-        feats = enc(x_nchw)
+        feats = enc(x_nchw, dist=self._dist) if self._dist is not None else enc(x_nchw)
         return ops.nchw_to_nhwc(feats.contiguous()), x_nchw
 
     @torch.no_grad()
@@ -286,8 +294,8 @@ class FaithDiffStableDiffusionXLPipeline:
                  callback_on_step_end_tensor_inputs=("latents",), add_sample=True, **kwargs):
         if not torch.cuda.is_available():
             raise RuntimeError("faithdiff_dev_b200 has no CPU path: a CUDA device is required")
-        if timesteps is not None or denoising_end is not None or cross_attention_kwargs or guidance_rescale:
-            raise NotImplementedError("custom timesteps / denoising_end / cross_attention_kwargs / guidance_rescale")
+        if timesteps is not None or cross_attention_kwargs or guidance_rescale:
+            raise NotImplementedError("custom timesteps / cross_attention_kwargs / guidance_rescale")
         if guidance_scale <= 1:
             raise NotImplementedError("the hot path implements the classifier-free-guidance branch (guidance_scale > 1)")
         height = height or self.default_sample_size * self.vae_scale_factor
@@ -296,10 +304,12 @@ class FaithDiffStableDiffusionXLPipeline:
         target_size = target_size or (height, width)
         self.check_inputs(lr_img, prompt, height, width, prompt_embeds, negative_prompt, negative_prompt_embeds,
                           pooled_prompt_embeds, negative_pooled_prompt_embeds)
-        if prompt_embeds is None:
-            prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
-                prompt, prompt_2, negative_prompt=negative_prompt, negative_prompt_2=negative_prompt_2, clip_skip=clip_skip,
-                num_images_per_prompt=num_images_per_prompt)
+        # always through encode_prompt: it returns given embeddings unchanged and builds the negative branch (zeros under
+        # force_zeros_for_empty_prompt, else the encoded negative prompt) when only the positive embeddings were passed
+        prompt_embeds, negative_prompt_embeds, pooled_prompt_embeds, negative_pooled_prompt_embeds = self.encode_prompt(
+            prompt, prompt_2, negative_prompt=negative_prompt, negative_prompt_2=negative_prompt_2, clip_skip=clip_skip,
+            num_images_per_prompt=num_images_per_prompt, prompt_embeds=prompt_embeds, negative_prompt_embeds=negative_prompt_embeds,
+            pooled_prompt_embeds=pooled_prompt_embeds, negative_pooled_prompt_embeds=negative_pooled_prompt_embeds)
         dev, dt = self.device, BF16
         unet, vae, sch = self.unet, self.vae, self.scheduler
         ev = {k: torch.cuda.Event(enable_timing=True) for k in ("t0", "enc", "loop", "dec")}
@@ -309,6 +319,11 @@ class FaithDiffStableDiffusionXLPipeline:
         lr_nhwc, _ = self._preprocess(lr_img, height, width)
         sch.set_timesteps(num_inference_steps, device="cpu")
         ts = sch.timesteps
+        if denoising_end is not None and isinstance(denoising_end, float) and 0 < denoising_end < 1:
+            # pipeline…:1297-1311: stop after the timesteps >= the cutoff (the returned sample keeps the remaining noise)
+            n_train = sch.config.num_train_timesteps
+            cutoff = int(round(n_train - denoising_end * n_train))
+            ts = ts[:int((ts >= cutoff).sum())]
         lq_nhwc, lr_nchw = self._encode_lq(lr_nhwc)
         h, w = height // 8, width // 8
         k = (target_size[0] // 8, target_size[1] // 8)
@@ -325,9 +340,15 @@ class FaithDiffStableDiffusionXLPipeline:
             latents = torch.randn(shape, generator=generator, device=gdev, dtype=dt).to(dev)
         latents = latents.to(dev) * sch.init_noise_sigma
         if start_point == "lr":
-            z0 = vae.encode(lr_nchw).latent_dist.sample() * vae.config.scaling_factor
+            enc_out = vae.encode(lr_nchw, dist=self._dist) if self._dist is not None else vae.encode(lr_nchw)
+            z0 = enc_out.latent_dist.sample() * vae.config.scaling_factor
             t0 = torch.randint(999, 1000, (1,), device=dev).long()
             latents = self.DDPM_scheduler.add_noise(z0[0:1], latents, t0)
+        if self.world_size > 1:
+            # every rank must blend the SAME x: rank 0's draw wins (see set_distributed)
+            latents = latents.contiguous()
+            src = torch.distributed.get_global_rank(self.process_group, 0) if self.process_group is not None else 0
+            torch.distributed.broadcast(latents, src=src, group=self.process_group)
         tiles = la.grids(latents.contiguous())                      # [T,4,k1,k2]
         weights, origins = la.weights64, la.origins
 
@@ -338,10 +359,12 @@ class FaithDiffStableDiffusionXLPipeline:
         # work units = (tile, CFG branch); contiguous balanced ranges per rank (a whole CFG pair per launch slot on 1 GPU)
         my_units = shard_units(T, self.rank, self.world_size)
         my_tiles = sorted({u // 2 for u in my_units})
-        cond = {}
-        for t in my_tiles:                                          # ControlNetConditioningEmbedding: once per tile
+        # ControlNetConditioningEmbedding: once per tile of this rank, kept as one tensor in tile order (launch groups are
+        # contiguous tile ranges, so a group's embeddings are a slice)
+        cond_all = torch.empty((len(my_tiles), k1, k2, unet.conv_in[0].shape[0]), device=dev, dtype=BF16)
+        for n_, t in enumerate(my_tiles):
             i, j = idx[t]
-            cond[t] = unet.condition_embed(lq_nhwc[:, i:i + k1, j:j + k2, :].contiguous())
+            cond_all[n_].copy_(unet.condition_embed(lq_nhwc[:, i:i + k1, j:j + k2, :].contiguous())[0])
         ids_all = torch.tensor([[original_size[0], original_size[1], i, j, target_size[0], target_size[1]] for i, j in idx],
                                dtype=torch.float32).to(dt).to(torch.float32)   # rounded through the working dtype
         temb_table = unet.time_embedding_table(ts, te, ids_all.to(dev))          # [S, T, 2, ΣC]: all (step, tile) biases
@@ -362,7 +385,9 @@ class FaithDiffStableDiffusionXLPipeline:
             key = (slot, branch)
             if key not in self._graphs:
                 self._graphs[key] = TileStepGraph(unet, kv, lk, slot, branch, k1, k2, dt, add_sample, self.use_cuda_graph)
-            plans.append((self._graphs[key], gt, torch.tensor(g, device=dev, dtype=torch.long)))
+            assert gt == list(range(gt[0], gt[-1] + 1)), "launch groups are contiguous tile ranges"
+            c_lo = my_tiles.index(gt[0])
+            plans.append((self._graphs[key], (gt[0], gt[-1] + 1), (c_lo, c_lo + len(gt)), torch.tensor(g, device=dev, dtype=torch.long)))
         for key, gobj in self._graphs.items():
             if key != "key":
                 gobj.set_text_kv(kv)
@@ -385,6 +410,7 @@ class FaithDiffStableDiffusionXLPipeline:
         eps = torch.empty((n_local,) + tuple(tiles.shape[1:]), device=dev, dtype=dt)     # unit order (pairs when 1 GPU)
         canvas_lowp = None
         peer = None
+        num = torch.empty(shape, device=dev, dtype=torch.float32) if self.world_size > 1 else None
         if self.world_size > 1 and os.environ.get("FD_P2P_EXCHANGE", "0") == "1":
             key = (tuple(shape), self.rank, self.world_size)
             if getattr(self, "_peer_key", None) != key:
@@ -398,8 +424,8 @@ class FaithDiffStableDiffusionXLPipeline:
             next_div = sch.step_scalars(i + 1)[2] if i + 1 < len(ts) else 1.0
             tval = ts[i]
             pos = 0
-            for gobj, gt, gu in plans:
-                gobj([scaled[t] for t in gt], [cond[t] for t in gt], temb_units[i].index_select(0, gu), eps[pos:pos + gobj.ns])
+            for gobj, (t_lo, t_hi), (c_lo, c_hi), gu in plans:
+                gobj(scaled[t_lo:t_hi], cond_all[c_lo:c_hi], temb_units[i].index_select(0, gu), eps[pos:pos + gobj.ns])
                 pos += gobj.ns
             if self.world_size == 1:
                 canvas, canvas_lowp, tiles, scaled = ops.cfg_euler_blend(eps.view((T, 2) + tuple(tiles.shape[1:])), tiles, weights,
@@ -414,12 +440,10 @@ class FaithDiffStableDiffusionXLPipeline:
                 tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)
                 scaled = ops.scale_div(tiles, next_div)
             else:
-                num = torch.zeros(shape, device=dev, dtype=torch.float32)
-                ops.unit_accumulate(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
+                # three launches: this rank's numerator (overwrite, no zero-fill), the exchange, divide + cast + re-tile + scale
+                ops.unit_numerator(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
                 exchange_canvas(num, self.process_group)
-                canvas, canvas_lowp = ops.canvas_finalize(num, count, dt)
-                tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)
-                scaled = ops.scale_div(tiles, next_div)
+                canvas, canvas_lowp, tiles, scaled = ops.canvas_finalize_retile(num, count, origins, k1, k2, next_div, dt)
             if callback_on_step_end is not None:
                 callback_on_step_end(self, i, tval, {"latents": canvas_lowp})
         latents = canvas_lowp
@@ -429,7 +453,7 @@ class FaithDiffStableDiffusionXLPipeline:
         else:
             # -- decode (pipeline…:1411-1451): latents / scaling_factor → VAE → u8
             z = latents / vae.config.scaling_factor
-            image = vae.decode(z, return_dict=False)[0]
+            image = (vae.decode(z, return_dict=False, dist=self._dist) if self._dist is not None else vae.decode(z, return_dict=False))[0]
             u8 = ops.image_postprocess(ops.nchw_to_nhwc(image.contiguous()), True)
             self._last_u8 = u8
             if output_type == "pil":

@@ -261,16 +261,19 @@ class UNet2DConditionModel:
         e = ops.conv3x3(g, ce["w1"], bias=ce["b1"], act=1)
         return ops.conv3x3(e, ce["w2"], bias=ce["b2"])
 
-    def stem(self, sample_nchw, cond_nhwc, add_sample=True, groups=1):
+    def stem(self, sample_nchw, cond_nhwc, add_sample=True, groups=1, cat=None):
         """conv_in + FaithDiff fusion (…extension.py:571-579).  sample NCHW [B,4,h,w]; cond NHWC [B,h,w,320] or
-        None.  The information transformer attends across the batch axis (seq = B // groups per pixel)."""
+        None.  The information transformer attends across the batch axis (seq = B // groups per pixel).
+        `cat` (optional, [B,h,w,2*c0]): caller-owned stem input whose upper channel half already holds the condition
+        embedding (the tile-step graph writes it there directly); conv_in fills the lower half."""
         B, _, h, w = sample_nchw.shape
         c0 = self.conv_in[0].shape[0]
-        if cond_nhwc is None:
+        if cond_nhwc is None and cat is None:
             return ops.conv3x3_small_in(sample_nchw.contiguous(), *self.conv_in)
-        cat = torch.empty((B, h, w, 2 * c0), device=self.device, dtype=BF16)
+        if cat is None:
+            cat = torch.empty((B, h, w, 2 * c0), device=self.device, dtype=BF16)
+            cat[..., c0:] = cond_nhwc        # strided D2D copy of the cached, step-invariant condition embedding
         ops.conv3x3_small_in(sample_nchw.contiguous(), *self.conv_in, out=cat[..., :c0])
-        cat[..., c0:] = cond_nhwc        # strided D2D copy of the cached, step-invariant condition embedding
         x = cat.view(B * h * w, 2 * c0)
         for blk in self.information_transformer_layes:
             x = blk(x, groups, B // groups, h * w)

@@ -54,9 +54,27 @@ def _count_blocks(sd, prefix):
     return n
 
 
-# multi-GPU context for the one-time tiled stages (set by the pipeline): tiles are independent up to the seam blend, so
-# rank r computes tiles r, r+W, … and every tile is broadcast from its owner before the (cheap, replicated) seam blend
-DIST = {"rank": 0, "world": 1, "group": None}
+class DistCtx:
+    """Multi-GPU context of the one-time tiled stages.  It belongs to a pipeline (`pipeline.set_distributed`) and is handed to
+    every encode / decode call (`dist=`), so two pipelines of one process (e.g. a 1-rank and an N-rank one over the same VAE)
+    do not share it.  Tiles are independent up to the seam blend: every rank computes a FLOP-balanced subset of the tiles, ONE
+    all-gather moves them, the (cheap) seam blend is replicated."""
+    __slots__ = ("rank", "world", "group")
+
+    def __init__(self, rank=0, world=1, group=None):
+        self.rank, self.world, self.group = rank, world, group
+
+
+def assign_tiles(areas, world):
+    """Owner rank of each tile, balanced by tile area (edge tiles are smaller, so round-robin is not balanced): largest tile
+    first onto the least-loaded rank; ties broken by tile index / rank, hence identical on every rank."""
+    load = [0] * world
+    owner = [0] * len(areas)
+    for idx in sorted(range(len(areas)), key=lambda i: (-areas[i], i)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[idx] = r
+        load[r] += areas[idx]
+    return owner
 
 
 def _down8(n):
@@ -70,26 +88,26 @@ def _down8(n):
 TILE_BATCH = 8
 
 
-def _tiled(x, fn, tile_in, stride, blend_extent, row_limit, out_shape=None):
+def _tiled(x, fn, tile_in, stride, blend_extent, row_limit, out_shape=None, dist=None):
     """Shared structure of Encoder.tiled_encode (…extension.py:164-190) and AutoencoderKL.tiled_encode/decode:
     row-major tiles, in-place seam cross-fade with the tile above then the tile to the left, crop, concat.
     Tiles are independent up to the seam blend, so equal-shaped tiles run as one batch."""
-    world, rank = DIST["world"], DIST["rank"]
+    world, rank = (dist.world, dist.rank) if dist is not None else (1, 0)
     shard = world > 1 and out_shape is not None
     bx = x.shape[0]
-    layout, mine, tiles = [], {}, {}
-    n = 0
+    layout, srcs = [], []
     for i in range(0, x.shape[2], stride):
         row = []
         for j in range(0, x.shape[3], stride):
-            src = x[:, :, i:i + tile_in, j:j + tile_in]
-            if not shard or n % world == rank:
-                mine.setdefault(tuple(src.shape), []).append((n, src))
-            else:
-                tiles[n] = torch.empty(out_shape(src.shape), device=x.device, dtype=x.dtype)
-            row.append(n)
-            n += 1
+            row.append(len(srcs))
+            srcs.append(x[:, :, i:i + tile_in, j:j + tile_in])
         layout.append(row)
+    n = len(srcs)
+    owner = assign_tiles([s.shape[2] * s.shape[3] for s in srcs], world) if shard else [rank] * n
+    mine, tiles = {}, {}
+    for idx, src in enumerate(srcs):
+        if owner[idx] == rank:
+            mine.setdefault(tuple(src.shape), []).append((idx, src))
     for items in mine.values():
         for k in range(0, len(items), TILE_BATCH):
             chunk = items[k:k + TILE_BATCH]
@@ -97,15 +115,25 @@ def _tiled(x, fn, tile_in, stride, blend_extent, row_limit, out_shape=None):
             for t, (idx, _) in enumerate(chunk):
                 tiles[idx] = out[t * bx:(t + 1) * bx]
     if shard:
-        # exchange AFTER all local tiles are enqueued, so the ranks compute concurrently (a broadcast placed between the
-        # computes would serialise the ranks on the stream)
-        grp = DIST["group"]
+        # ONE all-gather after all local tiles are enqueued (the ranks compute concurrently): every rank packs its tiles, in
+        # tile order, into a flat buffer padded to the largest rank's size; the other ranks' tiles are views into the result
+        shapes = [tuple(out_shape(s.shape)) for s in srcs]
+        numel = [sh[0] * sh[1] * sh[2] * sh[3] for sh in shapes]
+        per_rank = [sum(numel[i] for i in range(n) if owner[i] == r) for r in range(world)]
+        cap = max(per_rank)
+        send = torch.empty(cap, device=x.device, dtype=x.dtype)
+        pos = 0
         for idx in range(n):
-            owner = idx % world
-            src_rank = torch.distributed.get_global_rank(grp, owner) if grp is not None else owner
-            if not tiles[idx].is_contiguous():
-                tiles[idx] = tiles[idx].contiguous()
-            torch.distributed.broadcast(tiles[idx], src=src_rank, group=grp)
+            if owner[idx] == rank:
+                send[pos:pos + numel[idx]].copy_(tiles[idx].reshape(-1))
+                pos += numel[idx]
+        recv = torch.empty(world * cap, device=x.device, dtype=x.dtype)
+        torch.distributed.all_gather_into_tensor(recv, send, group=dist.group)
+        pos = [r * cap for r in range(world)]
+        for idx in range(n):
+            r = owner[idx]
+            tiles[idx] = recv[pos[r]:pos[r] + numel[idx]].view(shapes[idx])
+            pos[r] += numel[idx]
     out_rows = []
     for i, row in enumerate(layout):
         out = []
@@ -154,19 +182,20 @@ class Encoder:
         """NCHW in → NCHW out (1,512,H/8,W/8)."""
         return ops.nhwc_to_nchw(self.encode_nhwc(ops.nchw_to_nhwc(sample.contiguous())), sample.dtype)
 
-    def tiled_encode(self, x):
+    def tiled_encode(self, x, dist=None):
         stride = int(self.tile_sample_min_size * (1 - self.tile_overlap_factor))
         blend_extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
         row_limit = self.tile_latent_min_size - blend_extent
         c_out = self.mid[2].cout
         return _tiled(x, self.encode, self.tile_sample_min_size, stride, blend_extent, row_limit,
-                      out_shape=lambda s: (s[0], c_out, _down8(s[2]), _down8(s[3])))
+                      out_shape=lambda s: (s[0], c_out, _down8(s[2]), _down8(s[3])), dist=dist)
 
-    def forward(self, sample):
+    def forward(self, sample, dist=None):
+        """`dist` (a DistCtx, multi-GPU pipelines only) is an addition to the reference signature."""
         if not sample.is_cuda:
             raise RuntimeError("faithdiff_dev_b200 has no CPU path: input must be a CUDA tensor")
         if self.use_tiling and (sample.shape[-1] > self.tile_latent_min_size or sample.shape[-2] > self.tile_latent_min_size):
-            return self.tiled_encode(sample)
+            return self.tiled_encode(sample, dist)
         return self.encode(sample)
 
     __call__ = forward
@@ -259,7 +288,7 @@ class AutoencoderKL:
         m = ops.conv3x3_small_out(n, *self.e_conv_out, out_dtype=x.dtype, nchw_out=True)
         return ops.conv1x1_small(m, *self.quant)
 
-    def encode(self, x, return_dict=True):
+    def encode(self, x, return_dict=True, dist=None):
         if not x.is_cuda:
             raise RuntimeError("faithdiff_dev_b200 has no CPU path: input must be a CUDA tensor")
         if self.use_tiling and (x.shape[-1] > self.tile_sample_min_size or x.shape[-2] > self.tile_sample_min_size):
@@ -267,7 +296,7 @@ class AutoencoderKL:
             blend_extent = int(self.tile_latent_min_size * self.tile_overlap_factor)
             row_limit = self.tile_latent_min_size - blend_extent
             moments = _tiled(x, self._encode_moments, self.tile_sample_min_size, stride, blend_extent, row_limit,
-                             out_shape=lambda s: (s[0], 2 * self.config.latent_channels, _down8(s[2]), _down8(s[3])))
+                             out_shape=lambda s: (s[0], 2 * self.config.latent_channels, _down8(s[2]), _down8(s[3])), dist=dist)
         else:
             moments = self._encode_moments(x)
         return _EncOut(DiagonalGaussianDistribution(moments))
@@ -287,7 +316,7 @@ class AutoencoderKL:
         n = ops.groupnorm(x, *self.d_norm, self.config.norm_num_groups, 1e-6, True)
         return ops.conv3x3_small_out(n, *self.d_conv_out, out_dtype=z.dtype, nchw_out=nchw_out)
 
-    def decode(self, z, return_dict=True, generator=None):
+    def decode(self, z, return_dict=True, generator=None, dist=None):
         if not z.is_cuda:
             raise RuntimeError("faithdiff_dev_b200 has no CPU path: input must be a CUDA tensor")
         if self.use_tiling and (z.shape[-1] > self.tile_latent_min_size or z.shape[-2] > self.tile_latent_min_size):
@@ -296,7 +325,7 @@ class AutoencoderKL:
             row_limit = self.tile_sample_min_size - blend_extent
             up = 2 ** (len(self.config.block_out_channels) - 1)
             dec = _tiled(z, self._decode_tile, self.tile_latent_min_size, stride, blend_extent, row_limit,
-                         out_shape=lambda s: (s[0], self.config.out_channels, s[2] * up, s[3] * up))
+                         out_shape=lambda s: (s[0], self.config.out_channels, s[2] * up, s[3] * up), dist=dist)
         else:
             dec = self._decode_tile(z)
         if not return_dict:

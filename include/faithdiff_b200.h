@@ -98,6 +98,14 @@ int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, con
  * runs for encode_prompt — SURVEY §8f rank 1.                                                                          */
 int fd_attention_d64_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                             int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream);
+/* Single-head attention with head_dim 512 — the mid-block attention of the FaithDiff LQ Encoder and of the VAE
+ * (unet_2d_condition_vae_extension.py:96-106; diffusers Attention(heads=1, dim_head=512) inside UNetMidBlock2D): flash-style,
+ * S and P never leave the SM.  q/k/v/out: bf16 row views [batch*l, 512] with pitches ld* (elements, multiples of 8); softmax over
+ * the l keys of the same sample, scale = 512^-0.5 at the call sites.  Replaces the q·k^T GEMM -> fd_softmax_rows -> p·v GEMM
+ * sequence (which wrote the [l, l] fp32 score matrix to HBM) of round 1.                                                        */
+int fd_attention_d512(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out, int64_t ldo,
+                      int32_t batch, int32_t l, float scale, void* stream);
+
 
 /* row softmax: p[r, :] = softmax(alpha * s[r, :]) ; s fp32 [rows, ld_s], p bf16 [rows, ld_p]
  * (single-head d=512 attention of the VAE / LQ-encoder mid block, unet_…extension.py:96-106)              */
@@ -197,6 +205,16 @@ int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype
                        int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
 int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
                        int32_t lowp_dtype, int64_t n, void* stream);
+/* the N-rank step tail as three launches (the 1-rank tail is one, fd_cfg_euler_blend): fd_unit_numerator = fd_unit_accumulate
+ * that OVERWRITES canvas_num with this rank's contribution (no zero-fill pass); after the exchange fd_canvas_finalize_retile
+ * divides by the count map, casts, re-tiles (grids() of the next step, pipeline_FaithDiff_tlc.py:1326) and applies
+ * scale_model_input (:1336) — canvas_f32 / canvas_lowp optional, next_tiles / next_scaled [T,C,k1,k2] of `dtype`.          */
+int fd_unit_numerator(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+                      const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef, const int32_t* unit_addx,
+                      int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
+int fd_canvas_finalize_retile(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp, int32_t dtype,
+                              const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2,
+                              float next_scale_div, void* next_tiles, void* next_scaled, void* stream);
 /* The same exchange as ONE kernel over NVLink peer memory (opt-in, FD_P2P_EXCHANGE=1; peer_exchange.cu): every rank's numerator
  * canvas lives in a region all peers have mapped through CUDA IPC ([canvas parity 0][canvas parity 1][flags],
  * fd_peer_region_bytes(n)); the kernel publishes this rank's step flag to all peers, waits for theirs, sums the canvases in rank

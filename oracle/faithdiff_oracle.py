@@ -310,7 +310,7 @@ def pipeline_call(unet, vae, scheduler, ddpm_scheduler, lr_img, prompt_embeds, n
                   pooled_prompt_embeds, negative_pooled_prompt_embeds, height, width, num_inference_steps=20,
                   start_point="lr", overlap=0.5, guidance_scale=5.0, generator=None, target_size=(1024, 1024),
                   original_size=None, add_sample=True, output_type="pil", device="cpu", dtype=torch.float32,
-                  record=None):
+                  record=None, denoising_end=None):
     """Restates FaithDiffStableDiffusionXLPipeline.__call__ from the image preprocess (:1246) to postprocess
     (:1451); prompt encoding (:1231-1243, SURVEY §8f rank 1 'next') is replaced by injected embeddings.
     `record`, if a dict, receives per-step blended latents (the per-step parity quantity)."""
@@ -340,6 +340,10 @@ def pipeline_call(unet, vae, scheduler, ddpm_scheduler, lr_img, prompt_embeds, n
     pe = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0).to(device)
     te = torch.cat([negative_pooled_prompt_embeds, pooled_prompt_embeds], dim=0).to(device)
     T = latents.shape[0]
+    if denoising_end is not None and isinstance(denoising_end, float) and 0 < denoising_end < 1:   # :1297-1311
+        n_train = scheduler.config.num_train_timesteps
+        cutoff = int(round(n_train - denoising_end * n_train))
+        timesteps = timesteps[:len(list(filter(lambda ts: ts >= cutoff, timesteps)))]
     for i, t in enumerate(timesteps):                                      # :1324
         if i >= 1:
             latents = tlc_lat.grids(latents).to(dtype=latents.dtype)
@@ -357,6 +361,8 @@ def pipeline_call(unet, vae, scheduler, ddpm_scheduler, lr_img, prompt_embeds, n
                        added_cond_kwargs={"text_embeds": te, "time_ids": ids}, return_dict=False)[0]
             eu, et = eps.chunk(2)
             eps = eu + guidance_scale * (et - eu)                          # :1364-1365
+            if record is not None and s == 0:
+                record.setdefault("eps_std_first_tile", []).append((float(eu.float().std()), float(et.float().std()), float(eps.float().std())))
             sub = scheduler.step(eps, t, sub, generator=generator, return_dict=False)[0]
             status[s] = copy.deepcopy(scheduler.__dict__)
             out.append(sub)

@@ -185,6 +185,26 @@ def main():
     print("whole __call__ (20 tiles? no: %d tiles, 3 steps): reference == oracle (bit-exact)" % len(
         O.LocalAttention.tile_origins(20, 26, 16, 16, 0.5)[0]))
 
+    # denoising_end (pipeline…:1297-1311): the 20-step schedule cut after the timesteps >= 850 (3 steps) — assertion only
+    rec_ref.clear()
+    P.LocalAttention.grids_inverse = rec_inverse
+    torch.manual_seed(42)
+    out_ref = pipe(lr_img=lr_img, prompt="x", negative_prompt="", num_inference_steps=20, denoising_end=0.15, guidance_scale=5.0,
+                   generator=torch.Generator().manual_seed(42), start_point="lr", height=160, width=208, overlap=0.5,
+                   target_size=(128, 128)).images[0]
+    P.LocalAttention.grids_inverse = orig_inverse
+    rec = {}
+    torch.manual_seed(42)
+    out_ora = O.pipeline_call(ora_unet, vae, EulerDiscreteScheduler(), DDPMScheduler(), lr_img, pe, npe, pp, npp,
+                              160, 208, num_inference_steps=20, start_point="lr", overlap=0.5, guidance_scale=5.0,
+                              generator=torch.Generator().manual_seed(42), target_size=(128, 128), record=rec, denoising_end=0.15)[0]
+    assert len(rec_ref["step_latents"]) == 3 and len(rec["step_latents"]) == 3
+    for a, b in zip(rec_ref["step_latents"], rec["step_latents"]):
+        assert torch.equal(a.to(b.dtype), b)
+    assert np.array_equal(np.array(out_ref), np.array(out_ora))
+    manifest["pipeline_small"]["denoising_end_0.15_of_20_steps_checked"] = True
+    print("__call__ with denoising_end=0.15 of 20 steps (3 steps run): reference == oracle (bit-exact)")
+
     # ------------------------------------------------------------------ 5. scheduler known answers
     s = EulerDiscreteScheduler()
     s.set_timesteps(20)

@@ -26,19 +26,27 @@ pe, npe = torch.randn(1, 77, 256, generator=g), torch.randn(1, 77, 256, generato
 pp, npp = torch.randn(1, 64, generator=g), torch.randn(1, 64, generator=g)
 lr = O.synthetic_lq_image(328, 232, seed=0)
 lat = torch.randn(1, 4, 29, 41, generator=g).to(BF).cuda()
-def run(p):
-    torch.manual_seed(3)
+def run(p, seed, given_latents):
+    # RNG contract (pipeline.set_distributed): ranks may be seeded differently — rank 0's latents / posterior sample / DDPM noise
+    # are broadcast, so the N-rank run below (seed 3 + rank, latents drawn inside) must equal rank 0's 1-rank run with seed 3
+    torch.manual_seed(seed)
     return p(lr_img=lr, prompt_embeds=pe, negative_prompt_embeds=npe, pooled_prompt_embeds=pp, negative_pooled_prompt_embeds=npp,
              num_inference_steps=3, start_point="lr", height=232, width=328, overlap=0.5, guidance_scale=5.0, target_size=(128, 128),
-             latents=lat.clone(), output_type="u8").images[0]
-a = run(make_pipe(False)).float()
-b = run(make_pipe(True)).float()
-mse = ((a - b) ** 2).mean().item()
-psnr = 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
-allp = [None] * world
-torch.distributed.all_gather_object(allp, (psnr, float((a - b).abs().max())))
+             latents=lat.clone() if given_latents else None, generator=torch.Generator(device="cuda").manual_seed(seed),
+             output_type="u8").images[0]
+allp = []
+for given in (True, False):
+    a = run(make_pipe(False), 3, given).float()                    # 1-rank reference (every rank computes rank 0's: seed 3)
+    b = run(make_pipe(True), 3 + (0 if given else rank), given).float()
+    mse = ((a - b) ** 2).mean().item()
+    psnr = 99.0 if mse == 0 else 10 * np.log10(255 ** 2 / mse)
+    got = [None] * world
+    torch.distributed.all_gather_object(got, (psnr, float((a - b).abs().max()), float(b.sum())))
+    allp.append(got)
 if rank == 0:
-    print("world=%d: PSNR(N-rank vs 1-rank) per rank:" % world, allp, flush=True)
-    assert min(p for p, _ in allp) > 45, allp
+    print("world=%d: PSNR(N-rank vs 1-rank) per rank [latents given | drawn with per-rank seeds]:" % world, allp, flush=True)
+    for got in allp:
+        assert min(p for p, _, _ in got) > 45, allp
+        assert len({c for _, _, c in got}) == 1, ("ranks disagree on the N-rank image", got)
 torch.distributed.barrier()
 torch.distributed.destroy_process_group()

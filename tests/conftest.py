@@ -30,3 +30,27 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def _parity_path():
+    return os.environ.get("FD_PARITY_JSON") or os.path.join(ROOT, "gpurun_out", "r02_parity.json")
+
+
+@pytest.fixture
+def parity_record():
+    """record(name, **numbers): every measured parity error of the -m gpu suite goes into one JSON file (default
+    gpurun_out/r02_parity.json, which travels back from the GPU box; the committed copy is profiles/r02_parity.json) BEFORE
+    the test asserts on it, so a failing run still leaves its numbers behind."""
+    import json
+
+    def record(name, **numbers):
+        path = _parity_path()
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        try:
+            data = json.load(open(path))
+        except Exception:
+            data = {}
+        data[name] = numbers
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    return record

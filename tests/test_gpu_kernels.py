@@ -142,6 +142,27 @@ def test_attention_d64_growing_max(ops, lq, lk):
     assert rel(out, ref) < 1e-2
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("B,L,spread", [(2, 1024, 1.0), (1, 4096, 1.0), (3, 1000, 1.0), (1, 130, 1.0), (2, 7488, 1.0), (2, 700, 0.0)])
+def test_attention_d512(ops, B, L, spread):
+    """fd_attention_d512 (VAE / LQ-encoder mid block: one head, d = 512) against torch SDPA in fp32, through strided views of a
+    fused QKV buffer as the model calls it: token counts that are / are not multiples of the 128-key block (7488 = the 624x768-px
+    edge tile of the 4K layout), several samples per launch (keys of a neighbouring sample must not leak into the last block),
+    and — spread 0 — logits whose row maximum keeps growing along the key axis (in-place rescale of the TMEM-resident output)."""
+    torch.manual_seed(5)
+    qkv = torch.randn(B * L, 1536, device="cuda")
+    if spread == 0.0:
+        qkv[:, :512] *= 2.0
+        qkv[:, 512:1024] *= torch.linspace(0.2, 3.0, L, device="cuda").repeat(B)[:, None]
+    qkv = qkv.to(BF)
+    q, k, v = qkv[:, :512], qkv[:, 512:1024], qkv[:, 1024:]
+    out = ops.attention_d512(q, k, v, B, L, 512 ** -0.5)
+    r = lambda t: t.float().reshape(B, 1, L, 512)
+    ref = F.scaled_dot_product_attention(r(q), r(k), r(v)).reshape(B * L, 512)
+    assert torch.isfinite(out.float()).all()
+    assert rel(out, ref) < 1e-2
+
+
 @pytest.mark.parametrize("B,HW,C0,C1,silu", [(2, 1024, 320, 0, True), (2, 256, 1280, 640, True), (1, 4096, 64, 0, False), (3, 100, 32, 32, True)])
 def test_groupnorm(ops, B, HW, C0, C1, silu):
     torch.manual_seed(4)

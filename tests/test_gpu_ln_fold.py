@@ -1,15 +1,14 @@
-"""-m gpu, EXPERIMENTAL (skipped unless FD_TEST_EXPERIMENTAL=1): LayerNorm folded into the GEMMs around it (fd_gemm_ln,
-FD_LN_FOLD=1).  Not part of the default path; these tests are the acceptance bar for switching it on:
-producer statistics == row sums of the stored bf16 output; consumer == layer_norm(x) W^T + b (linear and GEGLU epilogues,
-single-CTA and CTA-pair tiles); a transformer stack with the fold on == the same stack with LayerNorm launches."""
+"""-m gpu: LayerNorm folded into the GEMMs around it (fd_gemm_ln; the DEFAULT path of the UNet's transformer blocks since round 2,
+FD_LN_FOLD=0 switches back to LayerNorm launches).  Producer statistics == row sums of the stored bf16 output; consumer ==
+layer_norm(x) W^T + b (linear and GEGLU epilogues, single-CTA and CTA-pair tiles); a transformer stack with the fold on == the
+same stack with LayerNorm launches."""
 import os
 
 import pytest
 import torch
 import torch.nn.functional as F
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("FD_TEST_EXPERIMENTAL") != "1", reason="opt-in path; set FD_TEST_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 BF = torch.bfloat16
 
 
