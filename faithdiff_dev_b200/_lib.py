@@ -71,13 +71,13 @@ _SIGS = {
     "fd_batch_axis_attention": [vp, vp, i32, i32, i64, i32, i32, vp],
     "fd_tile_gather": [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp],
     "fd_tile_blend": [vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp],
-    "fd_cfg_euler_blend": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp],
+    "fd_cfg_euler_blend": [vp, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp],
     "fd_tile_accumulate": [vp, vp, i32, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32, f32, vp, vp],
-    "fd_unit_accumulate": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "fd_unit_accumulate": [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
     "fd_canvas_finalize": [vp, vp, vp, vp, i32, i64, vp],
-    "fd_unit_numerator": [vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
-    "fd_canvas_finalize_retile": [vp, vp, vp, vp, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp],
-    "fd_scale_div": [vp, vp, i32, f32, i64, vp],
+    "fd_unit_numerator": [vp, i32, vp, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp],
+    "fd_canvas_finalize_retile": [vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp],
+    "fd_scale_div": [vp, i32, vp, i32, f32, i64, vp],
     "fd_peer_region_bytes": [i64],
     "fd_peer_alloc": [C.POINTER(vp), i64],
     "fd_peer_free": [vp],

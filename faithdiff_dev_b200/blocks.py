@@ -134,11 +134,34 @@ class Downsample:
         return ops.conv3x3(x, self.w, bias=self.b, stride=2, pad_lo=self.pad_lo)
 
 
+def upsample_phase_weights(w):
+    """[O,I,3,3] fp32 -> four [O, 4*I] bf16 operands, one per output phase (a, b) of conv3x3(nearest_upsample_2x(x)): along each
+    axis the three taps of phase 0 fall on input pixels {i-1, i, i} and of phase 1 on {i, i, i+1}, so the two taps that share a
+    pixel are summed (in fp32, one bf16 rounding of the sum); tap order r'*2 + s', channel-minor."""
+    def fold(t, axis, a):
+        t0, t1, t2 = t.select(axis, 0), t.select(axis, 1), t.select(axis, 2)
+        return torch.stack((t0, t1 + t2) if a == 0 else (t0 + t1, t2), dim=axis)
+    wf = w.float()
+    out = []
+    for a in range(2):
+        for b in range(2):
+            ph = fold(fold(wf, 2, a), 3, b)                                        # [O, I, 2, 2]
+            out.append(ph.permute(0, 2, 3, 1).reshape(ph.shape[0], -1).to(BF16).contiguous())
+    return out
+
+
 class Upsample:
+    """diffusers Upsample2D: nearest x2 (or to an explicit size) + conv3x3.  The x2 case runs as four phase convs straight from
+    the low-resolution tensor (ops.conv3x3_upsampled2x): no 4x tensor in HBM and 4/9 of the conv's FLOPs; FD_UPSAMPLE_FOLD=0 or
+    an explicit odd `size` (forward_upsample_size, …extension.py:665-666) takes the materialising path."""
+
     def __init__(self, W):
         self.w, self.b = W.conv3("conv.weight"), W.f32("conv.bias")
+        self.wp = upsample_phase_weights(W.raw("conv.weight").detach().to(W.device)) if os.environ.get("FD_UPSAMPLE_FOLD", "1") == "1" else None
 
     def __call__(self, x, size=None):
+        if size is None and self.wp is not None:
+            return ops.conv3x3_upsampled2x(x, self.wp, bias=self.b)
         u = ops.upsample_nearest(x) if size is None else ops.upsample_nearest(x, size[0], size[1])
         return ops.conv3x3(u, self.w, bias=self.b)
 

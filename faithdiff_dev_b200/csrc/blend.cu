@@ -47,7 +47,8 @@ __global__ void tile_gather_kernel(const uint8_t* __restrict__ canvas, uint8_t* 
 struct BlendParams {
   const void* tiles;      // mode 0: [T,C,k1,k2]; mode 1: current latents x [T,C,k1,k2]
   const void* eps;        // mode 1: UNet output [T,2,C,k1,k2]
-  int dtype;
+  int dtype;              // dtype of eps (mode 1) / of the tiles (mode 0): the model dtype, whose rounding the CFG arithmetic follows
+  int x_dtype;            // dtype of the latent state x (tiles in, next_tiles out): the model dtype (reference cast semantics) or fp32
   const double* weights;  // [k1,k2] fp64 (channel-invariant)
   const int* org;
   int ntiles, c, h, w, k1, k2;
@@ -71,14 +72,14 @@ __device__ __forceinline__ float euler_step(const BlendParams& p, int t, int ch,
   d = round_lowp(__fmul_rn(d, p.guidance), p.dtype);
   const float e = round_lowp(__fadd_rn(eu, d), p.dtype);
   // EulerDiscreteScheduler.step (gamma = 0): fp32 sample; sigma*eps rounded to the model dtype
-  const float x = load_lowp(p.tiles, p.dtype, ((long long)t * p.c + ch) * plane + off);
+  const float x = load_lowp(p.tiles, p.x_dtype, ((long long)t * p.c + ch) * plane + off);
   const float se = round_lowp(__fmul_rn(e, p.sigma), p.dtype);
   const float pred0 = __fsub_rn(x, se);
   // torch's CUDA true-divide by a host scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu); the
   // reference runs on CUDA, so that is the arithmetic reproduced here
   const float deriv = __fmul_rn(__fsub_rn(x, pred0), p.inv_sigma);
   const float dt = __fsub_rn(p.sigma_next, p.sigma);
-  return round_lowp(__fadd_rn(x, __fmul_rn(deriv, dt)), p.dtype);
+  return round_lowp(__fadd_rn(x, __fmul_rn(deriv, dt)), p.x_dtype);
 }
 
 __global__ void tile_blend_kernel(const BlendParams p) {
@@ -95,7 +96,7 @@ __global__ void tile_blend_kernel(const BlendParams p) {
       const double wgt = p.weights[(long long)ly * p.k2 + lx];
       float v;
       if (p.eps) v = euler_step(p, t, ch, ly, lx);
-      else v = load_lowp(p.tiles, p.dtype, ((long long)t * p.c + ch) * plane + (long long)ly * p.k2 + lx);
+      else v = load_lowp(p.tiles, p.x_dtype, ((long long)t * p.c + ch) * plane + (long long)ly * p.k2 + lx);
       pred = __double2float_rn(__dadd_rn((double)pred, __dmul_rn((double)v, wgt)));
       cnt = __double2float_rn(__dadd_rn((double)cnt, wgt));
     }
@@ -104,13 +105,13 @@ __global__ void tile_blend_kernel(const BlendParams p) {
     if (p.canvas_f32) p.canvas_f32[i] = r;
     if (p.canvas_lowp) store_lowp(p.canvas_lowp, p.lowp_dtype, i, r);
     if (p.next_tiles) {
-      const float rl = round_lowp(r, p.dtype);
+      const float rl = round_lowp(r, p.x_dtype);
       const float rs = round_lowp(__fmul_rn(rl, p.inv_next_div), p.dtype);
       for (int t = 0; t < p.ntiles; ++t) {
         const int ly = y - p.org[2 * t], lx = x - p.org[2 * t + 1];
         if (ly < 0 || ly >= p.k1 || lx < 0 || lx >= p.k2) continue;
         const long long o = ((long long)t * p.c + ch) * plane + (long long)ly * p.k2 + lx;
-        store_lowp(p.next_tiles, p.dtype, o, rl);
+        store_lowp(p.next_tiles, p.x_dtype, o, rl);
         if (p.next_scaled) store_lowp(p.next_scaled, p.dtype, o, rs);
       }
     }
@@ -121,7 +122,7 @@ __global__ void tile_blend_kernel(const BlendParams p) {
 //   x' = x + dt * ((1-g) * eps_uncond + g * eps_text)
 // so every unit deposits  w * coef_u * eps_u  (coef = (1-g)*dt or g*dt) and the branch-0 unit of a tile also deposits w * x.
 // Summed over all ranks (all-reduce) this is the blend numerator; fp32 combination (no intermediate bf16 roundings).
-__global__ void unit_accumulate_kernel(const void* __restrict__ x_tiles, const void* __restrict__ eps_units, int dtype,
+__global__ void unit_accumulate_kernel(const void* __restrict__ x_tiles, int x_dtype, const void* __restrict__ eps_units, int dtype,
                                        const double* __restrict__ weights, const int* __restrict__ org,
                                        const int* __restrict__ unit_tile, const float* __restrict__ unit_coef,
                                        const int* __restrict__ unit_addx, int nunits, int c, int h, int w, int k1, int k2,
@@ -139,7 +140,7 @@ __global__ void unit_accumulate_kernel(const void* __restrict__ x_tiles, const v
       if (ly < 0 || ly >= k1 || lx < 0 || lx >= k2) continue;
       const long long off = (long long)ly * k2 + lx;
       float v = __fmul_rn(unit_coef[u], load_lowp(eps_units, dtype, ((long long)u * c + ch) * plane + off));
-      if (unit_addx[u]) v = __fadd_rn(v, load_lowp(x_tiles, dtype, ((long long)t * c + ch) * plane + off));
+      if (unit_addx[u]) v = __fadd_rn(v, load_lowp(x_tiles, x_dtype, ((long long)t * c + ch) * plane + off));
       acc = __dadd_rn(acc, __dmul_rn((double)v, weights[off]));
     }
     canvas_num[i] = __double2float_rn(acc);
@@ -158,8 +159,8 @@ __global__ void canvas_finalize_kernel(const float* __restrict__ num, const floa
 // multi-GPU step tail after the exchange, one launch: divide by the count map, cast, re-tile (LocalAttention.grids of the next
 // step) and scale_model_input — the gather-form tail of tile_blend_kernel on an already summed numerator
 __global__ void canvas_finalize_retile_kernel(const float* __restrict__ num, const float* __restrict__ count, float* __restrict__ out,
-                                              void* lowp, int dtype, const int* __restrict__ org, int ntiles, int c, int h, int w,
-                                              int k1, int k2, float inv_next_div, void* next_tiles, void* next_scaled) {
+                                              void* lowp, int dtype, int x_dtype, const int* __restrict__ org, int ntiles, int c, int h,
+                                              int w, int k1, int k2, float inv_next_div, void* next_tiles, void* next_scaled) {
   const long long total = (long long)c * h * w;
   const long long plane = (long long)k1 * k2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -169,13 +170,13 @@ __global__ void canvas_finalize_retile_kernel(const float* __restrict__ num, con
     const float r = __fdiv_rn(num[i], count[i]);
     if (out) out[i] = r;
     if (lowp) store_lowp(lowp, dtype, i, r);
-    const float rl = round_lowp(r, dtype);
+    const float rl = round_lowp(r, x_dtype);
     const float rs = round_lowp(__fmul_rn(rl, inv_next_div), dtype);
     for (int t = 0; t < ntiles; ++t) {
       const int ly = y - org[2 * t], lx = x - org[2 * t + 1];
       if (ly < 0 || ly >= k1 || lx < 0 || lx >= k2) continue;
       const long long o = ((long long)t * c + ch) * plane + (long long)ly * k2 + lx;
-      store_lowp(next_tiles, dtype, o, rl);
+      store_lowp(next_tiles, x_dtype, o, rl);
       store_lowp(next_scaled, dtype, o, rs);
     }
   }
@@ -183,9 +184,9 @@ __global__ void canvas_finalize_retile_kernel(const float* __restrict__ num, con
 
 // scale_model_input: out = round_lowp(x * (1/div))  (EulerDiscreteScheduler.scale_model_input, pipeline…:1336; torch CUDA
 // divides by a host scalar through its fp32 reciprocal)
-__global__ void scale_div_kernel(const void* __restrict__ x, void* __restrict__ out, int dtype, float inv_div, long long n) {
+__global__ void scale_div_kernel(const void* __restrict__ x, int x_dtype, void* __restrict__ out, int dtype, float inv_div, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    store_lowp(out, dtype, i, __fmul_rn(load_lowp(x, dtype, i), inv_div));
+    store_lowp(out, dtype, i, __fmul_rn(load_lowp(x, x_dtype, i), inv_div));
 }
 
 // b[..., y, :] = a[..., -e+y, :] * (1 - y/e) + b[..., y, :] * (y/e)   (vertical) — torch rounding per op
@@ -240,18 +241,19 @@ extern "C" int fd_tile_blend(const void* tiles, int32_t tile_dtype, const double
                              int32_t lowp_dtype, void* stream_) {
   FD_REQUIRE(tiles && weights && org && (canvas_f32 || canvas_lowp), "fd_tile_blend: null pointer");
   BlendParams p = {};
-  p.tiles = tiles; p.dtype = tile_dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h; p.w = w;
-  p.k1 = k1; p.k2 = k2; p.canvas_f32 = canvas_f32; p.canvas_lowp = canvas_lowp; p.lowp_dtype = lowp_dtype;
+  p.tiles = tiles; p.dtype = tile_dtype; p.x_dtype = tile_dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h;
+  p.w = w; p.k1 = k1; p.k2 = k2; p.canvas_f32 = canvas_f32; p.canvas_lowp = canvas_lowp; p.lowp_dtype = lowp_dtype;
   return launch_blend(p, stream_);
 }
 
-extern "C" int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, const double* weights, const int32_t* org,
+extern "C" int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, int32_t x_dtype, const double* weights, const int32_t* org,
                                   int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float guidance,
                                   float sigma, float sigma_next, float next_scale_div, float* canvas_f32, void* canvas_lowp,
                                   void* next_tiles, void* next_scaled, void* stream_) {
   FD_REQUIRE(eps && x_tiles && weights && org, "fd_cfg_euler_blend: null pointer");
+  FD_REQUIRE(x_dtype == dtype || x_dtype == 2, "fd_cfg_euler_blend: the latent state is kept in the model dtype or in fp32");
   BlendParams p = {};
-  p.tiles = x_tiles; p.eps = eps; p.dtype = dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h; p.w = w;
+  p.tiles = x_tiles; p.eps = eps; p.dtype = dtype; p.x_dtype = x_dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h; p.w = w;
   p.k1 = k1; p.k2 = k2; p.guidance = guidance; p.sigma = sigma; p.sigma_next = sigma_next; p.inv_sigma = 1.0f / sigma;
   p.inv_next_div = 1.0f / next_scale_div;
   p.canvas_f32 = canvas_f32; p.canvas_lowp = canvas_lowp; p.lowp_dtype = dtype; p.next_tiles = next_tiles; p.next_scaled = next_scaled;
@@ -263,7 +265,7 @@ extern "C" int fd_tile_accumulate(const void* tiles, const void* eps, int32_t dt
                                   float sigma, float sigma_next, float* canvas_num, void* stream_) {
   FD_REQUIRE(tiles && weights && org && canvas_num, "fd_tile_accumulate: null pointer");
   BlendParams p = {};
-  p.tiles = tiles; p.eps = eps; p.dtype = dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h; p.w = w;
+  p.tiles = tiles; p.eps = eps; p.dtype = dtype; p.x_dtype = dtype; p.weights = weights; p.org = org; p.ntiles = ntiles; p.c = c; p.h = h; p.w = w;
   p.k1 = k1; p.k2 = k2; p.guidance = guidance; p.sigma = sigma; p.sigma_next = sigma_next; p.inv_sigma = 1.0f / sigma;
   p.canvas_num = canvas_num;
   p.accumulate_only = 1;
@@ -292,48 +294,48 @@ extern "C" int fd_seam_blend(const void* a, void* b, int32_t dtype, int32_t c, i
   return 0;
 }
 
-extern "C" int fd_scale_div(const void* x, void* out, int32_t dtype, float div, int64_t n, void* stream_) {
-  FD_REQUIRE(x && out && dtype >= 0 && dtype <= 2, "fd_scale_div: bad arguments");
-  scale_div_kernel<<<blend_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, out, dtype, 1.0f / div, n);
+extern "C" int fd_scale_div(const void* x, int32_t x_dtype, void* out, int32_t dtype, float div, int64_t n, void* stream_) {
+  FD_REQUIRE(x && out && dtype >= 0 && dtype <= 2 && x_dtype >= 0 && x_dtype <= 2, "fd_scale_div: bad arguments");
+  scale_div_kernel<<<blend_grid(n), 256, 0, (cudaStream_t)stream_>>>(x, x_dtype, out, dtype, 1.0f / div, n);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+extern "C" int fd_unit_accumulate(const void* x_tiles, int32_t x_dtype, const void* eps_units, int32_t dtype, const double* weights,
                                   const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef,
                                   const int32_t* unit_addx, int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1,
                                   int32_t k2, float* canvas_num, void* stream_) {
   FD_REQUIRE(x_tiles && eps_units && weights && origins_ij && unit_tile && unit_coef && unit_addx && canvas_num,
              "fd_unit_accumulate: null pointer");
   unit_accumulate_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
-      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 0);
+      x_tiles, x_dtype, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 0);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int fd_unit_numerator(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+extern "C" int fd_unit_numerator(const void* x_tiles, int32_t x_dtype, const void* eps_units, int32_t dtype, const double* weights,
                                  const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef,
                                  const int32_t* unit_addx, int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1,
                                  int32_t k2, float* canvas_num, void* stream_) {
   FD_REQUIRE(x_tiles && eps_units && weights && origins_ij && unit_tile && unit_coef && unit_addx && canvas_num,
              "fd_unit_numerator: null pointer");
   unit_accumulate_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
-      x_tiles, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 1);
+      x_tiles, x_dtype, eps_units, dtype, weights, origins_ij, unit_tile, unit_coef, unit_addx, nunits, c, h, w, k1, k2, canvas_num, 1);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int fd_canvas_finalize_retile(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
-                                         int32_t dtype, const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w,
-                                         int32_t k1, int32_t k2, float next_scale_div, void* next_tiles, void* next_scaled,
+                                         int32_t dtype, int32_t x_dtype, const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h,
+                                         int32_t w, int32_t k1, int32_t k2, float next_scale_div, void* next_tiles, void* next_scaled,
                                          void* stream_) {
-  FD_REQUIRE(canvas_num && count && origins_ij && next_tiles && next_scaled && dtype >= 0 && dtype <= 2,
+  FD_REQUIRE(canvas_num && count && origins_ij && next_tiles && next_scaled && dtype >= 0 && dtype <= 2 && (x_dtype == dtype || x_dtype == 2),
              "fd_canvas_finalize_retile: bad arguments");
   canvas_finalize_retile_kernel<<<blend_grid((long long)c * h * w), 256, 0, (cudaStream_t)stream_>>>(
-      canvas_num, count, canvas_f32, canvas_lowp, dtype, origins_ij, ntiles, c, h, w, k1, k2, 1.0f / next_scale_div, next_tiles,
+      canvas_num, count, canvas_f32, canvas_lowp, dtype, x_dtype, origins_ij, ntiles, c, h, w, k1, k2, 1.0f / next_scale_div, next_tiles,
       next_scaled);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());

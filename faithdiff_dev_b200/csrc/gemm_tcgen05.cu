@@ -660,7 +660,9 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
   const bool ln_in = ln && ln->stats_in, ln_out = ln && ln->stats_out;
   FD_REQUIRE(!(ln_in && ln_out), "fd_gemm_ln: one GEMM either consumes or produces row statistics");
   FD_REQUIRE(!(ln_in || ln_out) || (d->mode == 0 && !d->a[1]), "fd_gemm_ln: plain single-source GEMMs only");
-  FD_REQUIRE(d->mode >= 0 && d->mode <= 2, "fd_gemm: bad mode %d", d->mode);
+  FD_REQUIRE(d->mode >= 0 && d->mode <= 3, "fd_gemm: bad mode %d", d->mode);
+  FD_REQUIRE(d->mode != 3 || (!d->a[1] && !d->residual && !d->out_fp32 && d->pad_lo >= 0 && d->pad_lo <= 3),
+             "fd_gemm: mode 3 (3x3 conv over the 2x nearest-upsampled input, one output phase) takes one source, bf16 out, no residual");
   FD_REQUIRE(d->act >= 0 && d->act <= 5, "fd_gemm: bad act %d", d->act);
   GemmKParams p;
   memset(&p, 0, sizeof(p));
@@ -680,7 +682,7 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
 
   p.mode = d->mode == 0 ? 0 : 1;
   p.N = (int)d->N;
-  p.taps = d->mode == 0 ? 1 : 9;
+  p.taps = d->mode == 0 ? 1 : (d->mode == 3 ? 4 : 9);
   p.ctot = (int)ctot;
   p.kb_per_tap = (int)((c0 + kBlockK - 1) / kBlockK + (c1 + kBlockK - 1) / kBlockK);
   p.kb_src0 = (int)((c0 + kBlockK - 1) / kBlockK);
@@ -693,8 +695,10 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
     p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
   } else {
     const int H = d->in_h, W = d->in_w;
-    FD_REQUIRE(d->batch > 0 && H > 0 && W > 0 && (d->pad_lo == 0 || d->pad_lo == 1), "fd_gemm: bad conv geometry");
-    if (d->mode == 1) {
+    FD_REQUIRE(d->batch > 0 && H > 0 && W > 0 && (d->mode == 3 || d->pad_lo == 0 || d->pad_lo == 1), "fd_gemm: bad conv geometry");
+    if (d->mode == 3) {
+      p.out_h = H; p.out_w = W;          // the phase's output grid = the input grid (out pixel (2i+a, 2j+b) <-> input pixel (i, j))
+    } else if (d->mode == 1) {
       FD_REQUIRE(d->pad_lo == 1, "fd_gemm: stride-1 conv supports pad 1 only");
       p.out_h = H; p.out_w = W;
     } else {
@@ -708,7 +712,13 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
     M = (long long)d->batch * p.out_h * p.out_w;
     for (int t = 0; t < 9; ++t) {
       const int r = t / 3, s = t % 3;
-      if (d->mode == 1) {
+      if (d->mode == 3) {
+        // phase (a, b) of conv3x3(nearest_upsample_2x(x)): the three taps of an axis fall on TWO input pixels — a = 0: {i-1, i},
+        // a = 1: {i, i+1} — with the weights that share a pixel pre-summed on the host (tap t = r'*2 + s' of the [N, 4*C] operand)
+        if (t >= 4) continue;
+        const int a = d->pad_lo >> 1, b = d->pad_lo & 1;
+        p.tap_map[t] = 0; p.tap_dy[t] = (t >> 1) - 1 + a; p.tap_dx[t] = (t & 1) - 1 + b;
+      } else if (d->mode == 1) {
         p.tap_map[t] = 0; p.tap_dy[t] = r - 1; p.tap_dx[t] = s - 1;
       } else {
         const int ty = r - d->pad_lo, tx = s - d->pad_lo;
@@ -767,6 +777,7 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
     if (env_direct < 0) { const char* e = getenv("FD_GEMM_DIRECT_EPILOGUE"); env_direct = e ? atoi(e) : 0; }
     if (env_direct) p.tma_epi = 0;
   }
+  FD_REQUIRE(d->mode != 3 || p.tma_epi, "fd_gemm: mode 3 needs the TMA epilogue (bf16 output, 16-byte aligned rows)");
   p.slot_bytes = d->act == 2 ? 1024 : 2048;
   const int staging_bytes = p.tma_epi ? 16 * p.slot_bytes : 0;
   const int ln_strip_bytes = ln_in ? 8 * 128 * (int)sizeof(float) : 0;       // colsum strips of the 8 epilogue warps, after the barriers
@@ -784,7 +795,7 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
       if (encode_tensor_map(&p.amap[s], d->a[s], 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
                             CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
     }
-  } else if (d->mode == 1) {
+  } else if (d->mode == 1 || d->mode == 3) {
     for (int s = 0; s < nsrc; ++s) {
       const uint64_t ld = (uint64_t)d->a_ld[s];
       uint64_t dims[4] = {(uint64_t)d->a_cols[s], (uint64_t)d->in_w, (uint64_t)d->in_h, (uint64_t)d->batch};
@@ -830,6 +841,15 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
         uint64_t str[1] = {ld * 2};
         uint32_t box[2] = {box_c, 32};
         if (encode_tensor_map(map, base, 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, sw)) return 3;
+      } else if (d->mode == 3) {
+        // output phase (a, b): every second pixel of every second row of the [batch, 2H, 2W, N] image, starting at (a, b)
+        const int a = d->pad_lo >> 1, b = d->pad_lo & 1;
+        const uint64_t w2 = 2ull * p.out_w, h2 = 2ull * p.out_h;
+        const uint8_t* pb = (const uint8_t*)base + ((uint64_t)a * w2 + b) * ld * 2;
+        uint64_t dims[4] = {ncols, (uint64_t)p.out_w, (uint64_t)p.out_h, (uint64_t)d->batch};
+        uint64_t str[3] = {ld * 4, ld * 4 * w2, ld * 2 * w2 * h2};
+        uint32_t box[4] = {box_c, (uint32_t)box_w, (uint32_t)box_h, 1};
+        if (encode_tensor_map(map, pb, 4, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, sw)) return 3;
       } else {
         uint64_t dims[4] = {ncols, (uint64_t)p.out_w, (uint64_t)p.out_h, (uint64_t)d->batch};
         uint64_t str[3] = {ld * 2, ld * 2 * p.out_w, ld * 2 * p.out_w * p.out_h};

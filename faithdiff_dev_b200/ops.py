@@ -121,6 +121,30 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
     return out
 
 
+def conv3x3_upsampled2x(x, w_phases, bias=None, out=None):
+    """conv3x3(nearest_upsample_2x(x)) without the upsampled tensor: four launches, one per output phase (a, b), each a 2x2-tap
+    conv over x [B,H,W,C] with the phase's pre-summed weights w_phases[a*2+b] [N, 4*C] (blocks.upsample_phase_weights) writing
+    every second pixel of every second row of out [B,2H,2W,N]."""
+    assert x.dim() == 4 and x.dtype == BF16 and x.stride(3) == 1
+    B, H, W, C0 = x.shape
+    assert x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1), "NHWC images must be dense in B,H,W"
+    N = w_phases[0].shape[0]
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, N), device=x.device, dtype=BF16)
+    assert out.is_contiguous() and out.shape == (B, 2 * H, 2 * W, N)
+    for ph in range(4):
+        w = w_phases[ph]
+        assert w.is_contiguous() and w.shape == (N, 4 * C0)
+        d = GemmDesc()
+        d.a[0], d.a_cols[0], d.a_ld[0] = x.data_ptr(), C0, x.stride(2)
+        d.b, d.N, d.mode, d.batch, d.in_h, d.in_w, d.pad_lo = w.data_ptr(), N, 3, B, H, W, ph
+        if bias is not None:
+            d.bias = bias.data_ptr()
+        d.out, d.ld_out, d.alpha = out.data_ptr(), out.stride(2), 1.0
+        check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(upsampled conv)")
+    return out
+
+
 def attention(q, k, v, batch, heads, lq, lk, scale, out=None, causal=False):
     """q [batch*lq, >=heads*64] / k, v [batch*lk, ...] bf16 row views (unit inner stride) -> out [batch*lq, heads*64]."""
     if out is None:
@@ -319,14 +343,17 @@ def tile_blend(tiles, weights, origins, h, w, lowp_dtype=None):
 
 
 def cfg_euler_blend(eps, x_tiles, weights, origins, h, w, guidance, sigma, sigma_next, next_div, want_next=True):
+    """x_tiles in eps.dtype (the reference's per-step cast) or fp32 (latent state kept in fp32); -> (canvas fp32, canvas in the
+    model dtype, next tiles in x_tiles.dtype, next scaled tiles in the model dtype)."""
     T, c, k1, k2 = x_tiles.shape
-    dev, dt = x_tiles.device, x_tiles.dtype
+    dev, dt = x_tiles.device, eps.dtype
     canvas = torch.empty((1, c, h, w), device=dev, dtype=torch.float32)
     lowp = torch.empty((1, c, h, w), device=dev, dtype=dt)
     nxt = torch.empty_like(x_tiles) if want_next else None
-    nxs = torch.empty_like(x_tiles) if want_next else None
-    check(lib.fd_cfg_euler_blend(_p(eps), _p(x_tiles), _DT[dt], _p(weights), _p(origins), T, c, h, w, k1, k2, guidance, sigma,
-                                 sigma_next, next_div, _p(canvas), _p(lowp), _p(nxt), _p(nxs), _stream()), "fd_cfg_euler_blend")
+    nxs = torch.empty(x_tiles.shape, device=dev, dtype=dt) if want_next else None
+    check(lib.fd_cfg_euler_blend(_p(eps), _p(x_tiles), _DT[dt], _DT[x_tiles.dtype], _p(weights), _p(origins), T, c, h, w, k1, k2,
+                                 guidance, sigma, sigma_next, next_div, _p(canvas), _p(lowp), _p(nxt), _p(nxs), _stream()),
+          "fd_cfg_euler_blend")
     return canvas, lowp, nxt, nxs
 
 
@@ -340,28 +367,31 @@ def tile_accumulate(tiles, eps, weights, origins, canvas_num, guidance=0.0, sigm
 def unit_accumulate(x_tiles, eps_units, weights, origins, unit_tile, unit_coef, unit_addx, canvas_num):
     U, c, k1, k2 = eps_units.shape
     _, _, h, w = canvas_num.shape
-    check(lib.fd_unit_accumulate(_p(x_tiles), _p(eps_units), _DT[x_tiles.dtype], _p(weights), _p(origins), _p(unit_tile), _p(unit_coef),
-                                 _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()), "fd_unit_accumulate")
+    check(lib.fd_unit_accumulate(_p(x_tiles), _DT[x_tiles.dtype], _p(eps_units), _DT[eps_units.dtype], _p(weights), _p(origins),
+                                 _p(unit_tile), _p(unit_coef), _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()),
+          "fd_unit_accumulate")
 
 
 def unit_numerator(x_tiles, eps_units, weights, origins, unit_tile, unit_coef, unit_addx, canvas_num):
     """canvas_num := this rank's blend numerator (overwrites; no zero-fill needed)."""
     U, c, k1, k2 = eps_units.shape
     _, _, h, w = canvas_num.shape
-    check(lib.fd_unit_numerator(_p(x_tiles), _p(eps_units), _DT[x_tiles.dtype], _p(weights), _p(origins), _p(unit_tile), _p(unit_coef),
-                                _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()), "fd_unit_numerator")
+    check(lib.fd_unit_numerator(_p(x_tiles), _DT[x_tiles.dtype], _p(eps_units), _DT[eps_units.dtype], _p(weights), _p(origins),
+                                _p(unit_tile), _p(unit_coef), _p(unit_addx), U, c, h, w, k1, k2, _p(canvas_num), _stream()),
+          "fd_unit_numerator")
 
 
-def canvas_finalize_retile(num, count, origins, k1, k2, next_div, lowp_dtype):
-    """(canvas fp32, canvas lowp, next tiles, next scaled tiles) from the exchanged numerator: one launch."""
+def canvas_finalize_retile(num, count, origins, k1, k2, next_div, lowp_dtype, state_dtype=None):
+    """(canvas fp32, canvas lowp, next tiles in state_dtype, next scaled tiles in lowp_dtype) from the exchanged numerator."""
     _, c, h, w = num.shape
     T = origins.shape[0]
+    state_dtype = state_dtype or lowp_dtype
     out = torch.empty_like(num)
     lowp = torch.empty(num.shape, device=num.device, dtype=lowp_dtype)
-    nxt = torch.empty((T, c, k1, k2), device=num.device, dtype=lowp_dtype)
-    nxs = torch.empty_like(nxt)
-    check(lib.fd_canvas_finalize_retile(_p(num), _p(count), _p(out), _p(lowp), _DT[lowp_dtype], _p(origins), T, c, h, w, k1, k2,
-                                        next_div, _p(nxt), _p(nxs), _stream()), "fd_canvas_finalize_retile")
+    nxt = torch.empty((T, c, k1, k2), device=num.device, dtype=state_dtype)
+    nxs = torch.empty((T, c, k1, k2), device=num.device, dtype=lowp_dtype)
+    check(lib.fd_canvas_finalize_retile(_p(num), _p(count), _p(out), _p(lowp), _DT[lowp_dtype], _DT[state_dtype], _p(origins), T, c, h,
+                                        w, k1, k2, next_div, _p(nxt), _p(nxs), _stream()), "fd_canvas_finalize_retile")
     return out, lowp, nxt, nxs
 
 
@@ -373,9 +403,9 @@ def canvas_finalize(num, count, lowp_dtype):
     return out, lowp
 
 
-def scale_div(x, div):
-    out = torch.empty_like(x)
-    check(lib.fd_scale_div(_p(x), _p(out), _DT[x.dtype], div, x.numel(), _stream()), "fd_scale_div")
+def scale_div(x, div, out_dtype=None):
+    out = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    check(lib.fd_scale_div(_p(x), _DT[x.dtype], _p(out), _DT[out.dtype], div, x.numel(), _stream()), "fd_scale_div")
     return out
 
 

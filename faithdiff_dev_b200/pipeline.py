@@ -113,6 +113,11 @@ class FaithDiffStableDiffusionXLPipeline:
         self.rank, self.world_size, self.process_group = 0, 1, None
         self._dist = None
         self.tiles_per_launch = 8          # upper bound; the launch plan mixes group sizes 1..N by measured cost
+        # dtype of the latent state x between scheduler steps.  The reference casts it to the model dtype every step
+        # (pipeline…:1373 `.to(model_output.dtype)`, :1409) — fp16 there.  In bf16 (3 fewer mantissa bits) those casts alone let
+        # the iterated state drift to rel-L2 1.2e-2 from the fp32 result over 20 steps (profiles/r02_parity_unnormalised_eps.json),
+        # so the 2 MB state stays in fp32 by default; None reproduces the reference's per-step casts bit for bit.
+        self.latent_state_dtype = torch.float32
         self.use_cuda_graph = True
         self._graphs = {}
 
@@ -335,13 +340,14 @@ class FaithDiffStableDiffusionXLPipeline:
 
         # -- initial latents (torch RNG on purpose: seeds must reproduce the reference's Philox stream)
         shape = (1, vae.config.latent_channels, h, w)
+        sdt = self.latent_state_dtype or dt
         if latents is None:
             gdev = generator.device if generator is not None else dev
             latents = torch.randn(shape, generator=generator, device=gdev, dtype=dt).to(dev)
-        latents = latents.to(dev) * sch.init_noise_sigma
+        latents = latents.to(dev, sdt) * sch.init_noise_sigma
         if start_point == "lr":
             enc_out = vae.encode(lr_nchw, dist=self._dist) if self._dist is not None else vae.encode(lr_nchw)
-            z0 = enc_out.latent_dist.sample() * vae.config.scaling_factor
+            z0 = enc_out.latent_dist.sample().to(sdt) * vae.config.scaling_factor
             t0 = torch.randint(999, 1000, (1,), device=dev).long()
             latents = self.DDPM_scheduler.add_noise(z0[0:1], latents, t0)
         if self.world_size > 1:
@@ -405,7 +411,7 @@ class FaithDiffStableDiffusionXLPipeline:
 
         # -- denoising loop (pipeline…:1324-1409)
         s0, _, div0 = sch.step_scalars(0)
-        scaled = ops.scale_div(tiles, div0)
+        scaled = ops.scale_div(tiles, div0, out_dtype=dt)
         n_local = len(my_units)
         eps = torch.empty((n_local,) + tuple(tiles.shape[1:]), device=dev, dtype=dt)     # unit order (pairs when 1 GPU)
         canvas_lowp = None
@@ -437,15 +443,15 @@ class FaithDiffStableDiffusionXLPipeline:
                 num.zero_()
                 ops.unit_accumulate(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
                 canvas, canvas_lowp = peer.exchange_finalize(self._peer_step, count, dt)
-                tiles = ops.tile_gather(canvas_lowp, origins, k1, k2)
-                scaled = ops.scale_div(tiles, next_div)
+                tiles = ops.tile_gather(canvas if sdt == torch.float32 else canvas_lowp, origins, k1, k2)
+                scaled = ops.scale_div(tiles, next_div, out_dtype=dt)
             else:
                 # three launches: this rank's numerator (overwrite, no zero-fill), the exchange, divide + cast + re-tile + scale
                 ops.unit_numerator(tiles, eps, weights, origins, unit_tile, unit_coef[i], unit_addx, num)
                 exchange_canvas(num, self.process_group)
-                canvas, canvas_lowp, tiles, scaled = ops.canvas_finalize_retile(num, count, origins, k1, k2, next_div, dt)
+                canvas, canvas_lowp, tiles, scaled = ops.canvas_finalize_retile(num, count, origins, k1, k2, next_div, dt, sdt)
             if callback_on_step_end is not None:
-                callback_on_step_end(self, i, tval, {"latents": canvas_lowp})
+                callback_on_step_end(self, i, tval, {"latents": canvas if sdt == torch.float32 else canvas_lowp})
         latents = canvas_lowp
         ev["loop"].record()
         if output_type == "latent":

@@ -26,6 +26,10 @@ int64_t fd_launch_count(void);
  * mode 0  A = up to two row-major bf16 matrices concatenated along K           (Linear layers, 1x1 convs)
  * mode 1  A = implicit im2col of up to two NHWC bf16 images concatenated along C, 3x3 stride 1  (conv3x3)
  * mode 2  A = implicit im2col of one NHWC bf16 image, 3x3 stride 2             (Downsample2D)
+ * mode 3  one output phase (a, b) = (pad_lo >> 1, pad_lo & 1) of conv3x3(nearest-2x-upsample(x)) — Upsample2D, diffusers
+ *         `F.interpolate(scale_factor=2, mode="nearest")` + conv reached from unet_2d_condition_vae_extension.py:661-684 and
+ *         the VAE decoder: out[2i+a, 2j+b] sees only a 2x2 neighbourhood of x, so the 4x tensor is never materialised and the
+ *         contraction is 4*C deep instead of 9*C (B = the phase's pre-summed taps [N, 4*C]); out = the [batch, 2H, 2W, N] image
  * B = weights bf16 [N, taps*(C0+C1)] (tap-major, channel-minor; K contiguous).
  * Replaces: diffusers Conv2d/Linear reached from FaithDiff/models/unet_2d_condition_vae_extension.py:571-579,
  * :611-690 (conv_in…conv_out, ResnetBlock2D, Transformer2DModel projections, GEGLU feed-forward,
@@ -186,8 +190,12 @@ int fd_tile_blend(const void* tiles, int32_t tile_dtype, const double* weights, 
                   void* canvas_lowp, int32_t lowp_dtype, void* stream);
 /* fused per-step tail: CFG combine + Euler step per tile (diffusers rounding order) + Gaussian blend + cast
  * + re-tile + scale_model_input for the next step.  eps: UNet outputs NCHW [T,2,C,k1,k2] (uncond, text),
- * x_tiles: current latents [T,C,k1,k2] (lowp).  Writes canvas_f32, canvas_lowp, next_tiles, next_scaled.     */
-int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, const double* weights,
+ * x_tiles: current latents [T,C,k1,k2] of x_dtype.  Writes canvas_f32, canvas_lowp, next_tiles (x_dtype), next_scaled (dtype).
+ * dtype = the model dtype (eps, and the rounding of the CFG arithmetic, pipeline…:1365); x_dtype = dtype reproduces the
+ * reference's per-step cast of the latents to the model dtype (:1373 `.to(model_output.dtype)`, :1409) bit for bit; x_dtype = 2
+ * keeps the 2 MB latent state in fp32 between steps — the pipeline's default in bf16, whose 8-bit mantissa otherwise lets the
+ * iterated state random-walk away from the reference (fp16 has three more bits).                                              */
+int fd_cfg_euler_blend(const void* eps, const void* x_tiles, int32_t dtype, int32_t x_dtype, const double* weights,
                        const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1,
                        int32_t k2, float guidance, float sigma, float sigma_next, float next_scale_div,
                        float* canvas_f32, void* canvas_lowp, void* next_tiles, void* next_scaled, void* stream);
@@ -200,7 +208,7 @@ int fd_tile_accumulate(const void* tiles, const void* eps_or_null, int32_t dtype
 /* finer multi-GPU split into (tile, CFG-branch) units: CFG + Euler are linear in eps, so each unit u deposits
  * w * (unit_coef[u] * eps_u + unit_addx[u] * x_tile) into the fp32 numerator (coef = (1-g)*dt or g*dt; addx = 1 for the
  * uncond unit of a tile).  eps_units [nunits,C,k1,k2]; x_tiles [T,C,k1,k2]; unit_tile maps a unit to its tile.            */
-int fd_unit_accumulate(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+int fd_unit_accumulate(const void* x_tiles, int32_t x_dtype, const void* eps_units, int32_t dtype, const double* weights,
                        const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef, const int32_t* unit_addx,
                        int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
 int fd_canvas_finalize(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp,
@@ -209,11 +217,11 @@ int fd_canvas_finalize(const float* canvas_num, const float* count, float* canva
  * that OVERWRITES canvas_num with this rank's contribution (no zero-fill pass); after the exchange fd_canvas_finalize_retile
  * divides by the count map, casts, re-tiles (grids() of the next step, pipeline_FaithDiff_tlc.py:1326) and applies
  * scale_model_input (:1336) — canvas_f32 / canvas_lowp optional, next_tiles / next_scaled [T,C,k1,k2] of `dtype`.          */
-int fd_unit_numerator(const void* x_tiles, const void* eps_units, int32_t dtype, const double* weights,
+int fd_unit_numerator(const void* x_tiles, int32_t x_dtype, const void* eps_units, int32_t dtype, const double* weights,
                       const int32_t* origins_ij, const int32_t* unit_tile, const float* unit_coef, const int32_t* unit_addx,
                       int32_t nunits, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2, float* canvas_num, void* stream);
 int fd_canvas_finalize_retile(const float* canvas_num, const float* count, float* canvas_f32, void* canvas_lowp, int32_t dtype,
-                              const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2,
+                              int32_t x_dtype, const int32_t* origins_ij, int32_t ntiles, int32_t c, int32_t h, int32_t w, int32_t k1, int32_t k2,
                               float next_scale_div, void* next_tiles, void* next_scaled, void* stream);
 /* The same exchange as ONE kernel over NVLink peer memory (opt-in, FD_P2P_EXCHANGE=1; peer_exchange.cu): every rank's numerator
  * canvas lives in a region all peers have mapped through CUDA IPC ([canvas parity 0][canvas parity 1][flags],
@@ -230,7 +238,7 @@ int fd_peer_ipc_close(void* ptr);
 int fd_canvas_exchange_finalize(const void* const* regions, int32_t rank, int32_t world, int32_t parity, uint32_t step, int64_t n,
                                 const float* count, float* canvas_f32, void* canvas_lowp, int32_t lowp_dtype, void* stream);
 /* EulerDiscreteScheduler.scale_model_input (pipeline…:1336): out = x / sqrt(sigma^2+1), rounded to dtype         */
-int fd_scale_div(const void* x, void* out, int32_t dtype, float div, int64_t n, void* stream);
+int fd_scale_div(const void* x, int32_t x_dtype, void* out, int32_t dtype, float div, int64_t n, void* stream);
 /* VAE / LQ-encoder seam blend (Encoder.blend_v/blend_h, …extension.py:150-162): in-place linear cross-fade of
  * the first `extent` rows (vertical=1) or columns of b with the last `extent` of a; NCHW, dtype 0/1/2.        */
 int fd_seam_blend(const void* a, void* b, int32_t dtype, int32_t c, int32_t ah, int32_t aw, int32_t bh, int32_t bw,

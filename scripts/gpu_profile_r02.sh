@@ -15,3 +15,14 @@ python scripts/agg_traffic.py gpurun_out/r02_launches_tilestep7_unfiltered.csv g
 head -n 30 gpurun_out/r02_launches_tilestep7_unfiltered_summary.txt
 # 3. unfiltered share of every kernel in one whole 20-step 4K restoration (CUPTI activity records through torch.profiler)
 timeout 400 python scripts/dev_profile_shares.py 4k 20 > gpurun_out/r02_kernel_shares_4k.txt 2>&1; echo "shares rc=$?"; head -n 25 gpurun_out/r02_kernel_shares_4k.txt
+# 4. long-KV attention at the 4K bench's shape (14 samples x 10 heads x 4096 keys): --set full with source-level stall sampling
+timeout 120 python scripts/dev_attn_one.py 14 10 4096 4096 3 > gpurun_out/r02_attn_one.log 2>&1; echo "attn one rc=$?"; cat gpurun_out/r02_attn_one.log
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:attention_d64_kernel --launch-skip 3 -c 1 -o gpurun_out/r02_attn4096 \
+  python scripts/dev_attn_one.py 14 10 4096 4096 3 > gpurun_out/r02_attn_ncu.log 2>&1; echo "ncu attention rc=$?"
+ncu -i gpurun_out/r02_attn4096.ncu-rep --page raw --csv > gpurun_out/r02_ncu_attention_4096_raw.csv 2>/dev/null
+ncu -i gpurun_out/r02_attn4096.ncu-rep --page source --csv > gpurun_out/r02_ncu_attention_4096_source.csv 2>/dev/null
+# 5. d=512 attention (VAE / LQ-encoder mid block): TFLOP/s next to the round-1 GEMM-softmax-GEMM path, then one --set full capture
+timeout 200 python scripts/dev_attn512.py > gpurun_out/r02_attn512.log 2>&1; echo "attn512 rc=$?"; tail -n 6 gpurun_out/r02_attn512.log
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:attention_d512_kernel --launch-skip 4 -c 1 -o gpurun_out/r02_attn512 \
+  python scripts/dev_attn512.py > gpurun_out/r02_attn512_ncu.log 2>&1; echo "ncu attn512 rc=$?"
+ncu -i gpurun_out/r02_attn512.ncu-rep --page raw --csv > gpurun_out/r02_ncu_attention_d512_raw.csv 2>/dev/null

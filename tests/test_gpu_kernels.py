@@ -142,6 +142,25 @@ def test_attention_d64_growing_max(ops, lq, lk):
     assert rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 16, 64, 64), (3, 9, 7, 128, 96), (1, 32, 32, 640, 640), (14, 8, 8, 320, 320)])
+def test_conv3x3_over_nearest_upsample_folded(ops, B, H, W, C, N):
+    """fd_gemm mode 3 (Upsample2D = nearest x2 + conv3x3, …extension.py:661-684 / VAE decoder) == conv3x3 of the materialised
+    upsampled tensor: the four output phases as 2x2-tap convs with pre-summed weights, borders (zero padding of the UPSAMPLED
+    image) included, sizes that do not fill the 128-pixel tile patch."""
+    from faithdiff_dev_b200.blocks import upsample_phase_weights
+    torch.manual_seed(B * 100 + C)
+    x = torch.randn(B, H, W, C, device="cuda").to(BF)
+    w = (torch.randn(N, C, 3, 3, device="cuda") / (9 * C) ** 0.5)
+    b = torch.randn(N, device="cuda") * 0.1
+    out = ops.conv3x3_upsampled2x(x, upsample_phase_weights(w), bias=b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.to(BF).float(), b, padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < 6e-3
+    mat = ops.conv3x3(ops.upsample_nearest(x), w.permute(0, 2, 3, 1).reshape(N, -1).to(BF).contiguous(), bias=b)
+    assert rel(out, mat) < 6e-3
+
+
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("B,L,spread", [(2, 1024, 1.0), (1, 4096, 1.0), (3, 1000, 1.0), (1, 130, 1.0), (2, 7488, 1.0), (2, 700, 0.0)])
 def test_attention_d512(ops, B, L, spread):
