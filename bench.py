@@ -300,6 +300,7 @@ def main():
     ap.add_argument("--workload", default="4k")
     ap.add_argument("--tiles-per-launch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the N-rank vs 1-rank parity run after the timed region")
     ap.add_argument("--images", type=int, default=None, help="batch workloads: number of images (default: the workload's)")
     ap.add_argument("--denoise-steps", type=int, default=None, help="profiling only: override the workload's 20 scheduler steps "
                                                                       "(the JSON line then names the reduced workload)")
@@ -417,7 +418,7 @@ def main():
     # test box has one GPU, so this line is where the multi-GPU path's numerics are attested): per-step blended latents rel-L2
     # and final-image PSNR of rank 0's N-rank restoration vs the single-rank pipeline over the same modules.
     parity = None
-    if world > 1 and not batch_mode:
+    if world > 1 and not batch_mode and not args.no_parity:
         lat_n, lat_1 = [], []
         img_n = restore(dev_u8, callback=(lambda p_, i, t, kw: lat_n.append(kw["latents"].float().clone())) if rank == 0 else None)
         torch.cuda.synchronize()
@@ -502,6 +503,7 @@ def main():
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
             "parity_n_rank_vs_1_rank": parity}))
     if world > 1:
+        pipe.shutdown()
         torch.distributed.destroy_process_group()
 
 

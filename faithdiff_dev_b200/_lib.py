@@ -28,6 +28,7 @@ class GemmLnDesc(C.Structure):
         ("stats_in", C.c_void_p), ("stats_in_ld", C.c_int64), ("stats_in_n", C.c_int32), ("pad0_", C.c_int32),
         ("colsum", C.c_void_p), ("inv_c", C.c_float), ("eps", C.c_float),
         ("stats_out", C.c_void_p), ("stats_out_ld", C.c_int64), ("stats_out_n", C.c_int32), ("pad1_", C.c_int32),
+        ("colstats_out", C.c_void_p), ("colstats_ld", C.c_int64), ("colstats_boxes", C.c_int32), ("colstats_boxes_per_image", C.c_int32),
     ]
 
 
@@ -59,6 +60,7 @@ _SIGS = {
     "fd_groupnorm_nhwc": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "fd_groupnorm_sync_bytes": [],
     "fd_groupnorm_nhwc_fused": [vp, i32, vp, i32, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp, vp],
+    "fd_groupnorm_nhwc_from_stats": [vp, i32, vp, i64, i32, i32, i64, vp, i32, vp, i64, i32, i32, i64, vp, vp, vp, i32, i64, i32, f32, i32, vp, vp],
     "fd_layernorm": [vp, vp, vp, vp, i64, i32, f32, vp],
     "fd_axpby_bf16": [vp, i64, vp, i64, vp, i64, i64, i32, f32, f32, vp],
     "fd_upsample_nearest_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, vp],

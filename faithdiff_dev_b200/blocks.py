@@ -71,7 +71,7 @@ class ResnetBlock:
         rb = None
         if self.tw is not None:
             rb = temb_all[:, self.temb_offset:self.temb_offset + self.cout]
-        h = ops.conv3x3(n1, self.c1w, bias=self.c1b, rowbias=rb)
+        h = ops.conv3x3(n1, self.c1w, bias=self.c1b, rowbias=rb, colstats=True)      # statistics for norm2 from the epilogue
         n2 = ops.groupnorm(h, self.n2g, self.n2b, self.groups, self.eps, True)
         if self.sw is not None:
             M = B * H * Wd
@@ -80,7 +80,7 @@ class ResnetBlock:
         else:
             assert x2 is None
             res = x
-        return ops.conv3x3(n2, self.c2w, bias=self.c2b, residual=res)
+        return ops.conv3x3(n2, self.c2w, bias=self.c2b, residual=res, colstats=True)   # ... for whichever GroupNorm reads the block's output
 
 
 class VaeAttention:
@@ -106,7 +106,8 @@ class VaeAttention:
         if Cc == 512 and os.environ.get("FD_VAE_ATTN_GEMM", "0") != "1":
             qkv = ops.gemm(n.reshape(B * L, Cc), self.wqkv, bias=self.bqkv)
             a = ops.attention_d512(qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], B, L, Cc ** -0.5)
-            return ops.gemm(a, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc)).view(B, H, Wd, Cc)
+            o = ops.gemm(a, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc), colstats_rows_per_sample=L)
+            return ops.tag_stats(o.view(B, H, Wd, Cc), getattr(o, "_fd_colstats", None))
         out = torch.empty_like(x)
         Lp = (L + 7) // 8 * 8            # token count padded to the 16-byte vector width of the GEMM epilogue
         for b in range(B):
@@ -131,7 +132,7 @@ class Downsample:
         self.w, self.b, self.pad_lo = W.conv3("conv.weight"), W.f32("conv.bias"), pad_lo
 
     def __call__(self, x):
-        return ops.conv3x3(x, self.w, bias=self.b, stride=2, pad_lo=self.pad_lo)
+        return ops.conv3x3(x, self.w, bias=self.b, stride=2, pad_lo=self.pad_lo, colstats=True)
 
 
 def upsample_phase_weights(w):
@@ -161,9 +162,9 @@ class Upsample:
 
     def __call__(self, x, size=None):
         if size is None and self.wp is not None:
-            return ops.conv3x3_upsampled2x(x, self.wp, bias=self.b)
+            return ops.conv3x3_upsampled2x(x, self.wp, bias=self.b, colstats=True)
         u = ops.upsample_nearest(x) if size is None else ops.upsample_nearest(x, size[0], size[1])
-        return ops.conv3x3(u, self.w, bias=self.b)
+        return ops.conv3x3(u, self.w, bias=self.b, colstats=True)
 
 
 def interleave_geglu(w, b):
@@ -272,5 +273,5 @@ class Transformer2D:
             h = ops.gemm(n.reshape(B * L, Cc), self.wi, bias=self.bi)
             for blk, kv in zip(self.blocks, kv_list):
                 h = blk(h, B, L, kv, lk)
-        out = ops.gemm(h, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc))
-        return out.view(B, H, Wd, Cc)
+        out = ops.gemm(h, self.wo, bias=self.bo, residual=x.reshape(B * L, Cc), colstats_rows_per_sample=L)
+        return ops.tag_stats(out.view(B, H, Wd, Cc), getattr(out, "_fd_colstats", None))

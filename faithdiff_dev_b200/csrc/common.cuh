@@ -88,13 +88,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting thread is parked by the hardware until the phase completes (or the hint expires)
+// instead of re-polling every ~25 clocks — the polling of the single-thread producer / MMA warps took issue slots from the
+// softmax / epilogue warps of the same scheduler (profiles/r02_ncu_attention_4096_source.csv: 16.4 M polls of p_full per launch).
+// FD_MBAR_SPIN (compile-time) restores the plain polling loop for A/B builds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef FD_MBAR_SPIN
   asm volatile(
       "{\n.reg .pred p;\nWAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)),
       "r"(parity)
       : "memory");
+#else
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+#endif
 }
 
 // TMA tile loads (global -> shared, completes on an mbarrier)

@@ -53,6 +53,10 @@ struct GemmKParams {
   float ln_inv_c, ln_eps;
   float2* ln_stats_out;
   int ln_out_ld;
+  // GroupNorm statistics from the producer (kLn = 3): per (32-row epilogue box, column pair) sum / sum of squares of the
+  // bf16-rounded outputs, float2 [4 * m_tiles, gn_ld]; the consumer GroupNorm becomes a single streaming pass (norm.cu)
+  float2* gn_stats_out;
+  int gn_ld;
 };
 
 constexpr int kBlockM = 128;
@@ -502,6 +506,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
           }
           fence_proxy_async();
           __syncwarp();
+          if constexpr (kLn == 3) {
+            // column-pair sums over this warp's 32 rows, read back from the staging slot (what the consumer will read: the
+            // ROUNDED values): lane = (pair, row parity); rows 2k + parity are 64 B apart, so a warp-wide load is conflict-free
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            const int pr = lane & 15, hf = lane >> 4;
+            const uint8_t* colp = slot + (pr & 3) * 4;
+            const int g8c = pr >> 2;
+            uint64_t s2 = 0ull, q2 = 0ull;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) {
+              const int rr = 2 * k2 + hf;
+              uint32_t u = *reinterpret_cast<const uint32_t*>(colp + rr * 64 + ((g8c ^ ((rr >> 1) & 3)) << 4));
+              if (!((vmask >> rr) & 1u)) u = 0u;
+              const uint64_t f = pack_f2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+              s2 = add_f2(s2, f);
+              q2 = fma_f2(f, f, q2);
+            }
+            float sa, sb, qa, qb;
+            unpack_f2(s2, sa, sb);
+            unpack_f2(q2, qa, qb);
+            float ssum = sa + sb, qsum = qa + qb;
+            ssum += __shfl_xor_sync(0xffffffffu, ssum, 16);
+            qsum += __shfl_xor_sync(0xffffffffu, qsum, 16);
+            if (hf == 0 && n0 + 2 * pr < p.N)
+              p.gn_stats_out[(long long)(m_blk * 4 + quad) * p.gn_ld + (n0 >> 1) + pr] = make_float2(ssum, qsum);
+            __syncwarp();                           // lane 0 may re-arm the slot for a residual load below
+          }
           if (lane == 0) {
             const int oc = act == 2 ? (n0 >> 1) : n0;
             if (p.mode == 0) tma_store_2d(&p.omap, slot, oc, box_row0);
@@ -657,8 +688,8 @@ using namespace fd;
 static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   FD_REQUIRE(d && d->a[0] && d->b && d->out, "fd_gemm: null operand");
-  const bool ln_in = ln && ln->stats_in, ln_out = ln && ln->stats_out;
-  FD_REQUIRE(!(ln_in && ln_out), "fd_gemm_ln: one GEMM either consumes or produces row statistics");
+  const bool ln_in = ln && ln->stats_in, ln_out = ln && ln->stats_out, gn_out = ln && ln->colstats_out;
+  FD_REQUIRE(!(ln_in && ln_out) && !(gn_out && (ln_in || ln_out)), "fd_gemm_ln: one GEMM either consumes or produces one kind of statistics");
   FD_REQUIRE(!(ln_in || ln_out) || (d->mode == 0 && !d->a[1]), "fd_gemm_ln: plain single-source GEMMs only");
   FD_REQUIRE(d->mode >= 0 && d->mode <= 3, "fd_gemm: bad mode %d", d->mode);
   FD_REQUIRE(d->mode != 3 || (!d->a[1] && !d->residual && !d->out_fp32 && d->pad_lo >= 0 && d->pad_lo <= 3),
@@ -890,7 +921,14 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
     p.ln_stats_out = (float2*)ln->stats_out; p.ln_out_ld = (int)ln->stats_out_ld;
     ln->stats_out_n = 2 * p.n_tiles;
   }
+  if (gn_out) {
+    FD_REQUIRE(epi == 1 && d->N % 2 == 0 && ln->colstats_ld >= d->N / 2, "fd_gemm_ln: column statistics need the linear TMA epilogue");
+    p.gn_stats_out = (float2*)ln->colstats_out; p.gn_ld = (int)ln->colstats_ld;
+    ln->colstats_boxes = 4 * p.m_tiles;
+    ln->colstats_boxes_per_image = d->mode == 0 ? 0 : 4 * p.tiles_per_img;
+  }
   using KernelFn = void (*)(GemmKParams);
+  static const KernelFn kernels_gn[2] = {gemm_tcgen05_kernel<false, 1, 3>, gemm_tcgen05_kernel<true, 1, 3>};
   static const KernelFn kernels_ln[6] = {gemm_tcgen05_kernel<false, 1, 1>, gemm_tcgen05_kernel<false, 2, 1>, gemm_tcgen05_kernel<false, 1, 2>,
                                          gemm_tcgen05_kernel<true, 1, 1>,  gemm_tcgen05_kernel<true, 2, 1>,  gemm_tcgen05_kernel<true, 1, 2>};
   static const KernelFn kernels[6] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
@@ -910,6 +948,14 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
       ln_attr_set = true;
     }
     kernel = kernels_ln[(p.pair ? 3 : 0) + (ln_out ? 2 : epi - 1)];
+  }
+  if (gn_out) {
+    static bool gn_attr_set = false;
+    if (!gn_attr_set) {
+      for (int i = 0; i < 2; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels_gn[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gn_attr_set = true;
+    }
+    kernel = kernels_gn[p.pair ? 1 : 0];
   }
   if (csize == 1) {
     const int grid = num_super < sms ? num_super : sms;

@@ -374,6 +374,117 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// GroupNorm(+SiLU) from PRODUCER statistics: the conv / GEMM that wrote x left per-(32-row box, channel pair) sums of the
+// bf16-rounded outputs (gemm_tcgen05_kernel<.., 1, 3>), so the normalisation is ONE streaming pass — no statistics read of x,
+// no grid-wide wait, no second DRAM read of a > L2 tensor.  (1) gn_stats_finalize_kernel, one CTA per (sample, group): fp64
+// combine of the group's box partials of up to two concatenated sources, in box order (deterministic), -> per-(sample, channel)
+// scale / shift; (2) gn_apply_stream_kernel: y = silu(x*scale + shift), 8 16-byte loads in flight per thread.
+struct GnStatSrc {
+  const float2* stats;   // [segments * seg_stride_boxes, ld] (sum, sum of squares) per (box, channel pair)
+  long long ld;
+  int boxes_per_sample, segments;
+  long long seg_stride_boxes;
+};
+
+__global__ void __launch_bounds__(256) gn_stats_finalize_kernel(GnStatSrc s0, int c0, GnStatSrc s1, int c1, int groups, long long hw,
+                                                                float eps, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                int silu, float* __restrict__ scale, float* __restrict__ shift) {
+  __shared__ double red[2][8];
+  __shared__ float s_mean, s_rstd;
+  const int b = blockIdx.x / groups, g = blockIdx.x - b * groups;
+  const int ct = c0 + c1, cpg = ct / groups;
+  const int pair_lo = g * cpg / 2, pair_hi = (g + 1) * cpg / 2;      // cpg is even: a pair never straddles two groups
+  double s = 0.0, q = 0.0;
+  for (int src = 0; src < 2; ++src) {
+    const GnStatSrc& S = src ? s1 : s0;
+    const int base_pair = src ? c0 / 2 : 0, npairs_src = (src ? c1 : c0) / 2;
+    const int lo = max(pair_lo - base_pair, 0), hi = min(pair_hi - base_pair, npairs_src);
+    if (!S.stats || lo >= hi) continue;
+    const long long nbox = (long long)S.boxes_per_sample * S.segments;
+    for (long long i = threadIdx.x; i < nbox; i += blockDim.x) {
+      const long long seg = i / S.boxes_per_sample, r = i - seg * S.boxes_per_sample;
+      const float2* row = S.stats + (seg * S.seg_stride_boxes + (long long)b * S.boxes_per_sample + r) * S.ld;
+      float fs = 0.f, fq = 0.f;
+      for (int pp = lo; pp < hi; ++pp) {
+        const float2 t = __ldg(row + pp);
+        fs += t.x;
+        fq += t.y;
+      }
+      s += (double)fs;
+      q += (double)fq;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { ts += red[0][w]; tq += red[1][w]; }
+    const double n = (double)hw * cpg;
+    const double mean = ts / n;
+    double var = tq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean = (float)mean;
+    s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float half = silu ? 0.5f : 1.f;            // SiLU as h + h*tanh(h), h = y/2 folded into the affine (see norm2)
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += blockDim.x) {
+    const float sc = s_rstd * gamma[c];
+    scale[(long long)b * ct + c] = sc * half;
+    shift[(long long)b * ct + c] = (beta[c] - s_mean * sc) * half;
+  }
+}
+
+// grid = cps chunks x batch; block = V*R threads (V = Ct/8 channel vectors, R pixel rows in flight); thread = one channel vector
+__global__ void __launch_bounds__(kGnFusedThreads, 2)
+gn_apply_stream_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat16* __restrict__ x1, int c1, long long hw, int R,
+                       const float* __restrict__ scale, const float* __restrict__ shift, int silu, __nv_bfloat16* __restrict__ out, int cps) {
+  const int b = blockIdx.x / cps, m = blockIdx.x - b * cps;
+  const int ct = c0 + c1, V = ct >> 3;
+  const int v = threadIdx.x % V, r = threadIdx.x / V;
+  if (r >= R) return;
+  const int ch = v * 8;
+  const bool from0 = ch < c0;
+  const int pitch = from0 ? c0 : c1;
+  const long long per = (hw + cps - 1) / cps;
+  const long long p0 = ((long long)m * per < hw) ? (long long)m * per : hw;
+  const long long p1 = (p0 + per < hw) ? p0 + per : hw;
+  const long long n = (p0 + r < p1) ? (p1 - p0 - r + R - 1) / R : 0;
+  if (n <= 0) return;
+  const __nv_bfloat16* ptr = (from0 ? x0 + (long long)b * hw * c0 + ch : x1 + (long long)b * hw * c1 + (ch - c0)) + (p0 + r) * pitch;
+  __nv_bfloat16* dst = out + ((long long)b * hw + p0 + r) * ct + ch;
+  const long long stride = (long long)R * pitch, ostride = (long long)R * ct;
+  const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * ct + ch));
+  const float4 a1 = __ldg(reinterpret_cast<const float4*>(scale + (long long)b * ct + ch + 4));
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + (long long)b * ct + ch));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(shift + (long long)b * ct + ch + 4));
+  const uint64_t a[4] = {pack_f2(a0.x, a0.y), pack_f2(a0.z, a0.w), pack_f2(a1.x, a1.y), pack_f2(a1.z, a1.w)};
+  const uint64_t sft[4] = {pack_f2(b0.x, b0.y), pack_f2(b0.z, b0.w), pack_f2(b1.x, b1.y), pack_f2(b1.z, b1.w)};
+  const uint64_t pol = l2_policy(2);               // x is dead after this pass: evict_first leaves the L2 to the output
+  auto run = [&](auto silu_tag) {
+    constexpr bool kSilu = decltype(silu_tag)::value;
+    long long k = 0;
+    for (; k + 8 <= n; k += 8) {
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = ld16_hint(ptr + j * stride, pol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(dst + j * ostride) = norm8<kSilu>(u[j], a, sft);
+      ptr += 8 * stride;
+      dst += 8 * ostride;
+    }
+    for (; k < n; ++k, ptr += stride, dst += ostride) *reinterpret_cast<uint4*>(dst) = norm8<kSilu>(ld16_hint(ptr, pol), a, sft);
+  };
+  if (silu) run(std::true_type{}); else run(std::false_type{});
+}
+
 // (Measured and dropped: the same kernel in packed fp32x2 arithmetic - 4 instead of 7.5 lane-instructions per element - was
 // no faster inside the tile-step graph (25.9 vs 25.0 us per launch) and slower for 640-wide rows (register pressure: 94-118
 // registers, two CTAs per SM); the bulk-copy pipelined variant below is slower still.  Both are kept out of the default path.)
@@ -656,6 +767,40 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
       (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
       (__nv_bfloat16*)out, partial, (unsigned*)sync, batch, cps, keep_frac);
   ++g_launches;
+  FD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fd_groupnorm_nhwc_from_stats(const void* x0, int32_t c0, const void* stats0, int64_t ld0, int32_t boxes_per_sample0,
+                                            int32_t segments0, int64_t seg_stride0, const void* x1, int32_t c1, const void* stats1,
+                                            int64_t ld1, int32_t boxes_per_sample1, int32_t segments1, int64_t seg_stride1,
+                                            const float* gamma, const float* beta, void* out, int32_t batch, int64_t hw, int32_t groups,
+                                            float eps, int32_t silu, float* work, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x1) c1 = 0;
+  const int ct = c0 + c1;
+  FD_REQUIRE(x0 && stats0 && out && work && gamma && beta && (!x1 || stats1), "fd_groupnorm_nhwc_from_stats: null pointer");
+  FD_REQUIRE(c0 % 8 == 0 && c1 % 8 == 0 && ct % groups == 0 && (ct / groups) % 2 == 0,
+             "fd_groupnorm_nhwc_from_stats: channels %d+%d groups %d unsupported (channels per group must be even)", c0, c1, groups);
+  const int V = ct / 8;
+  FD_REQUIRE(V <= kGnFusedThreads, "fd_groupnorm_nhwc_from_stats: too many channels");
+  GnStatSrc s0 = {(const float2*)stats0, ld0, boxes_per_sample0, segments0 > 0 ? segments0 : 1, seg_stride0};
+  GnStatSrc s1 = {(const float2*)stats1, ld1, boxes_per_sample1, segments1 > 0 ? segments1 : 1, seg_stride1};
+  float* scale = work;
+  float* shift = work + (int64_t)batch * ct;
+  gn_stats_finalize_kernel<<<dim3(batch * groups), dim3(256), 0, stream>>>(s0, c0, s1, c1, groups, (long long)hw, eps, gamma, beta,
+                                                                          (int)silu, scale, shift);
+  int R = kGnFusedThreads / V;
+  if (R < 1) R = 1;
+  const int threads = ((V * R + 31) / 32) * 32;
+  long long cps = (4ll * num_sms()) / batch;                           // two full waves of the 2-CTAs-per-SM slots, never a ragged third ...
+  if (cps < 1) cps = 1;
+  const long long max_cps = (hw + 8ll * R - 1) / (8ll * R);           // ... but at least 8 pixels per thread
+  if (cps > max_cps) cps = max_cps;
+  if (cps < 1) cps = 1;
+  gn_apply_stream_kernel<<<dim3((unsigned)(cps * batch)), dim3(threads), 0, stream>>>(
+      (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, R, scale, shift, (int)silu, (__nv_bfloat16*)out, (int)cps);
+  g_launches += 2;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

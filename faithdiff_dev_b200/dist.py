@@ -108,7 +108,7 @@ class PeerCanvas:
         assert self.n % 4 == 0, "canvas size must be a multiple of 4 floats"
         self.n_pad = (self.n + 63) // 64 * 64
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self._lib, self._check, self._C = lib, check, C
+        self._lib, self._check, self._C, self._group = lib, check, C, group
         mine = C.c_void_p()
         check(lib.fd_peer_alloc(C.byref(mine), lib.fd_peer_region_bytes(self.n)), "fd_peer_alloc")
         self._mine = mine.value
@@ -144,8 +144,14 @@ class PeerCanvas:
         return out, lowp
 
     def close(self):
+        """Collective: every rank must call it.  A peer may still be inside its last exchange kernel reading THIS rank's region
+        over P2P (completion of my own kernel only proves the peers have started theirs), so all ranks synchronise, meet at a
+        barrier and synchronise again before any handle is closed or freed."""
         C = self._C
         torch.cuda.synchronize()
+        if torch.distributed.is_initialized():
+            torch.distributed.barrier(group=self._group)
+            torch.cuda.synchronize()
         for q in self._opened:
             self._lib.fd_peer_ipc_close(C.c_void_p(q))
         self._opened = []

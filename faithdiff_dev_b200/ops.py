@@ -32,8 +32,48 @@ class RowStats:
         self.slots, self.n = slots, n          # fp32 [M, ld, 2] tensor; number of valid slots per row
 
 
+class ColStats:
+    """Per-(32-row box, channel pair) (sum, sum of squares) a producer conv / GEMM leaves for the GroupNorm that consumes its
+    output (fd_gemm_ln colstats_out -> fd_groupnorm_nhwc_from_stats).  Travels as the `_fd_colstats` attribute of the output
+    tensor object; any op that makes a new tensor drops it and the consumer falls back to the two-pass GroupNorm."""
+    __slots__ = ("buf", "ld", "boxes_per_sample", "segments", "seg_stride")
+
+    def __init__(self, buf, ld, boxes_per_sample, segments=1, seg_stride=0):
+        self.buf, self.ld, self.boxes_per_sample, self.segments, self.seg_stride = buf, ld, boxes_per_sample, segments, seg_stride
+
+    def select_samples(self, index, n_src):
+        """Statistics of x.index_select(0, index) for x of n_src samples (single segment)."""
+        assert self.segments == 1
+        b = self.buf[:n_src * self.boxes_per_sample].view(n_src, self.boxes_per_sample, self.ld, 2).index_select(0, index)
+        return ColStats(b.reshape(-1, self.ld, 2).contiguous(), self.ld, self.boxes_per_sample)
+
+
+GN_STATS = __import__("os").environ.get("FD_GN_STATS", "1") == "1"
+
+
+def tag_stats(t, st):
+    if st is not None:
+        t._fd_colstats = st
+    return t
+
+
+def _conv_tiles(H, W):
+    """Tiles per image of the implicit-GEMM conv (gemm_tcgen05.cu pick_patch: the 128-pixel patch w x 128/w that wastes least)."""
+    best, tiles = None, 0
+    w = 128
+    while w >= 8:
+        h = 128 // w
+        tx, ty = (W + w - 1) // w, (H + h - 1) // h
+        waste = (tx * w) * (ty * h) / float(W * H)
+        if best is None or waste < best - 1e-9:
+            best, tiles = waste, tx * ty
+        w >>= 1
+    return tiles
+
+
 def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None, act=0, out=None, out_fp32=False,
-         alpha=1.0, bias_along_m=False, block_n=0, ln_in=None, ln_colsum=None, ln_eps=1e-5, stats_out=False):
+         alpha=1.0, bias_along_m=False, block_n=0, ln_in=None, ln_colsum=None, ln_eps=1e-5, stats_out=False,
+         colstats_rows_per_sample=0):
     """out[M,N] = epilogue(alpha * [a | a2] @ w^T).  a/a2: bf16 [M,K*] (unit inner stride); w: bf16 [N,K] contiguous.
     LayerNorm folding (opt-in): `stats_out=True` returns (out, RowStats of out); `ln_in=RowStats of a` with
     `ln_colsum` = row sums of w (= W*gamma) computes LayerNorm(a) W^T + bias' without the LayerNorm pass."""
@@ -59,6 +99,15 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
         assert residual.dtype == BF16 and residual.stride(1) == 1
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(0)
     d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(0), alpha, block_n
+    if (GN_STATS and colstats_rows_per_sample and colstats_rows_per_sample % 128 == 0 and M % colstats_rows_per_sample == 0 and act == 0
+            and out.dtype == BF16 and not bias_along_m and ln_in is None and not stats_out and N % 16 == 0):
+        # GroupNorm statistics for the consumer of `out`: per (32-row box, column pair), tiles never straddle a sample
+        lnd = GemmLnDesc()
+        buf = torch.empty(((M + 127) // 128 * 4, N // 2, 2), device=a.device, dtype=torch.float32)
+        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), N // 2
+        check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(colstats)")
+        assert lnd.colstats_boxes == buf.shape[0]
+        return tag_stats(out, ColStats(buf, N // 2, colstats_rows_per_sample // 32))
     if ln_in is None and not stats_out:
         check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm")
         return out
@@ -85,8 +134,10 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
 _LN_SLOTS = {}
 
 
-def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0, alpha=1.0):
-    """3x3 conv on NHWC bf16 x [B,H,W,C] (optionally channel-concatenated with x2); w packed [N, 9*(C+C2)]."""
+def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride=1, pad_lo=1, out=None, block_n=0, alpha=1.0,
+            colstats=False):
+    """3x3 conv on NHWC bf16 x [B,H,W,C] (optionally channel-concatenated with x2); w packed [N, 9*(C+C2)].
+    colstats: also leave GroupNorm statistics of the output for its consumer (ColStats, attribute of the returned tensor)."""
     assert x.dim() == 4 and x.dtype == BF16 and x.stride(3) == 1
     B, H, W, C0 = x.shape
     assert x.stride(1) == W * x.stride(2) and x.stride(0) == H * x.stride(1), "NHWC images must be dense in B,H,W"
@@ -117,11 +168,19 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
         assert residual.dtype == BF16 and residual.stride(3) == 1
         d.residual, d.ld_res = residual.data_ptr(), residual.stride(2)
     d.out, d.ld_out, d.alpha, d.block_n = out.data_ptr(), out.stride(2), alpha, block_n
+    if colstats and GN_STATS and act == 0 and N % 16 == 0:
+        lnd = GemmLnDesc()
+        bps = 4 * _conv_tiles(Ho, Wo)
+        buf = torch.empty((B * bps, N // 2, 2), device=x.device, dtype=torch.float32)
+        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), N // 2
+        check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(conv, colstats)")
+        assert lnd.colstats_boxes == buf.shape[0] and lnd.colstats_boxes_per_image == bps, (lnd.colstats_boxes, buf.shape, bps)
+        return tag_stats(out, ColStats(buf, N // 2, bps))
     check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(conv)")
     return out
 
 
-def conv3x3_upsampled2x(x, w_phases, bias=None, out=None):
+def conv3x3_upsampled2x(x, w_phases, bias=None, out=None, colstats=False):
     """conv3x3(nearest_upsample_2x(x)) without the upsampled tensor: four launches, one per output phase (a, b), each a 2x2-tap
     conv over x [B,H,W,C] with the phase's pre-summed weights w_phases[a*2+b] [N, 4*C] (blocks.upsample_phase_weights) writing
     every second pixel of every second row of out [B,2H,2W,N]."""
@@ -132,6 +191,10 @@ def conv3x3_upsampled2x(x, w_phases, bias=None, out=None):
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, N), device=x.device, dtype=BF16)
     assert out.is_contiguous() and out.shape == (B, 2 * H, 2 * W, N)
+    st = None
+    if colstats and GN_STATS and N % 16 == 0:
+        bps = 4 * _conv_tiles(H, W)                    # per phase: the phase's output grid is the input grid
+        st = ColStats(torch.empty((4 * B * bps, N // 2, 2), device=x.device, dtype=torch.float32), N // 2, bps, 4, B * bps)
     for ph in range(4):
         w = w_phases[ph]
         assert w.is_contiguous() and w.shape == (N, 4 * C0)
@@ -141,8 +204,14 @@ def conv3x3_upsampled2x(x, w_phases, bias=None, out=None):
         if bias is not None:
             d.bias = bias.data_ptr()
         d.out, d.ld_out, d.alpha = out.data_ptr(), out.stride(2), 1.0
-        check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(upsampled conv)")
-    return out
+        if st is not None:
+            lnd = GemmLnDesc()
+            lnd.colstats_out, lnd.colstats_ld = st.buf[ph * st.seg_stride:].data_ptr(), N // 2
+            check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(upsampled conv, colstats)")
+            assert lnd.colstats_boxes == st.seg_stride
+        else:
+            check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(upsampled conv)")
+    return tag_stats(out, st)
 
 
 def attention(q, k, v, batch, heads, lq, lk, scale, out=None, causal=False):
@@ -181,6 +250,16 @@ def groupnorm(x, gamma, beta, groups, eps, silu, x2=None, out=None):
     hw = x.numel() // (B * C0)
     if out is None:
         out = torch.empty(x.shape[:-1] + (C0 + c1,), device=x.device, dtype=BF16)
+    st0, st1 = getattr(x, "_fd_colstats", None), getattr(x2, "_fd_colstats", None) if x2 is not None else None
+    if GN_STATS and st0 is not None and (x2 is None or st1 is not None) and ((C0 + c1) // groups) % 2 == 0 and (C0 + c1) // 8 <= 320:
+        # one streaming pass: the producers of x (and x2) left the statistics
+        work = torch.empty(2 * B * (C0 + c1), device=x.device, dtype=torch.float32)
+        a1 = (_p(x2), c1, _p(st1.buf), st1.ld, st1.boxes_per_sample, st1.segments, st1.seg_stride) if x2 is not None else \
+            (None, 0, None, 0, 0, 1, 0)
+        check(lib.fd_groupnorm_nhwc_from_stats(_p(x), C0, _p(st0.buf), st0.ld, st0.boxes_per_sample, st0.segments, st0.seg_stride, *a1,
+                                               _p(gamma), _p(beta), _p(out), B, hw, groups, eps, int(silu), _p(work), _stream()),
+              "fd_groupnorm_nhwc_from_stats")
+        return out
     work = torch.empty(lib.fd_groupnorm_work_floats(B, groups, C0 + c1), device=x.device, dtype=torch.float32)
     check(lib.fd_groupnorm_nhwc_fused(_p(x), C0, _p(x2), c1, _p(gamma), _p(beta), _p(out), B, hw, groups, eps, int(silu),
                                       _p(work), _p(_gn_sync(x.device)), _stream()), "fd_groupnorm_nhwc_fused")

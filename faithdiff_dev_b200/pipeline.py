@@ -80,6 +80,9 @@ class TileStepGraph:
             x2 = x1.unsqueeze(1).expand(-1, 2, -1, -1, -1).reshape((self.ns,) + tuple(x1.shape[1:])).contiguous()
         else:
             x2 = x1.index_select(0, self.gather_idx)
+        st = getattr(x1, "_fd_colstats", None)          # GroupNorm statistics of the stem output follow the sample gather
+        if st is not None:
+            ops.tag_stats(x2, st.select_samples(self.gather_idx, self.nt))
         self.eps = u.trunk(x2, self.temb, self.kv, self.lk, self.scaled.dtype)                  # [ns,4,k1,k2]
 
     def __call__(self, scaled_tiles, cond_tiles, temb_rows, eps_out):
@@ -120,6 +123,12 @@ class FaithDiffStableDiffusionXLPipeline:
         self.latent_state_dtype = torch.float32
         self.use_cuda_graph = True
         self._graphs = {}
+
+    def shutdown(self):
+        """Releases the opt-in peer-memory exchange region (collective over the ranks; a no-op otherwise)."""
+        if getattr(self, "_peer", None) is not None:
+            self._peer.close()
+            self._peer, self._peer_key = None, None
 
     # ------------------------------------------------------------------ reference-facing knobs
     def to(self, device=None, *a, **k):

@@ -278,8 +278,8 @@ class UNet2DConditionModel:
         for blk in self.information_transformer_layes:
             x = blk(x, groups, B // groups, h * w)
         res = cat.view(B * h * w, 2 * c0)[:, :c0] if add_sample else None
-        out = ops.gemm(x, *self.spatial_ch_projs[:1], bias=self.spatial_ch_projs[1], residual=res)
-        return out.view(B, h, w, c0)
+        out = ops.gemm(x, *self.spatial_ch_projs[:1], bias=self.spatial_ch_projs[1], residual=res, colstats_rows_per_sample=h * w)
+        return ops.tag_stats(out.view(B, h, w, c0), getattr(out, "_fd_colstats", None))
 
     def trunk(self, x, temb_all, kv, lk, out_dtype):
         """down / mid / up / out (…extension.py:611-690) on NHWC bf16."""

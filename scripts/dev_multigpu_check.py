@@ -13,10 +13,12 @@ cfg = O.TINY_UNET_CONFIG
 sd = arch.random_state_dict(arch.unet_param_shapes(cfg, lq_channels=64, encoder_channels=(32, 64, 64, 64)), seed=1, device="cuda")
 unet = fd.UNet2DConditionModel(**cfg); unet.load_state_dict(sd)
 vae = fd.AutoencoderKL(**O.TINY_VAE_CONFIG); vae.load_state_dict(arch.random_state_dict(arch.vae_param_shapes(dict(O.TINY_VAE_CONFIG, layers_per_block=2, latent_channels=4)), seed=2))
+pipes = []
 def make_pipe(dist):
     p = fd.FaithDiffStableDiffusionXLPipeline(vae, unet.denoise_encoder, None, None, None, None, unet, fd.EulerDiscreteScheduler(), fd.DDPMScheduler())
     if dist: p.set_distributed(rank, world)
     else: p.set_distributed(0, 1)
+    pipes.append(p)
     return p
 for e in (unet.denoise_encoder,):
     e.tile_sample_min_size, e.tile_latent_min_size, e.use_tiling = 128, 16, True
@@ -49,4 +51,6 @@ if rank == 0:
         assert min(p for p, _, _ in got) > 45, allp
         assert len({c for _, _, c in got}) == 1, ("ranks disagree on the N-rank image", got)
 torch.distributed.barrier()
+for p in pipes:
+    p.shutdown()
 torch.distributed.destroy_process_group()

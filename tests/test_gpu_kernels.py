@@ -142,6 +142,45 @@ def test_attention_d64_growing_max(ops, lq, lk):
     assert rel(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("kind,B,H,W,C,N,C2", [("conv", 3, 24, 40, 64, 320, 0), ("conv", 2, 32, 32, 320, 640, 320), ("conv_s2", 2, 33, 31, 128, 128, 0),
+                                               ("up", 2, 16, 16, 128, 640, 0), ("gemm", 2, 32, 32, 64, 320, 0), ("conv", 14, 8, 8, 64, 1280, 0),
+                                               ("conv", 1, 128, 128, 64, 128, 0)])
+def test_groupnorm_from_producer_statistics(ops, kind, B, H, W, C, N, C2):
+    """GroupNorm(+SiLU) as ONE streaming pass over statistics the producing conv / GEMM epilogue left behind (fd_gemm_ln colstats
+    -> fd_groupnorm_nhwc_from_stats) == the two-pass GroupNorm of the same tensor == torch: 3x3 convs whose pixel patches do not
+    tile the image, stride 2, the four phases of the folded upsampling conv, a plain GEMM producer, and a second concatenated
+    source with its own producer (a group then straddles both sources)."""
+    from faithdiff_dev_b200.blocks import upsample_phase_weights
+    if not ops.GN_STATS:
+        pytest.skip("FD_GN_STATS=0")
+    torch.manual_seed(N + H)
+    x = torch.randn(B, H, W, C, device="cuda").to(BF)
+    b = torch.randn(N, device="cuda")
+    if kind == "conv":
+        y = ops.conv3x3(x, (torch.randn(N, 9 * C, device="cuda") / (9 * C) ** 0.5).to(BF), bias=b, colstats=True)
+    elif kind == "conv_s2":
+        y = ops.conv3x3(x, (torch.randn(N, 9 * C, device="cuda") / (9 * C) ** 0.5).to(BF), bias=b, stride=2, pad_lo=0, colstats=True)
+    elif kind == "up":
+        y = ops.conv3x3_upsampled2x(x, upsample_phase_weights(torch.randn(N, C, 3, 3, device="cuda") / (9 * C) ** 0.5), bias=b, colstats=True)
+    else:
+        o = ops.gemm(x.reshape(B * H * W, C), (torch.randn(N, C, device="cuda") / C ** 0.5).to(BF), bias=b, colstats_rows_per_sample=H * W)
+        y = ops.tag_stats(o.view(B, H, W, N), o._fd_colstats)
+    assert getattr(y, "_fd_colstats", None) is not None
+    y2 = None
+    if C2:
+        y2 = ops.conv3x3(torch.randn(B, y.shape[1], y.shape[2], 64, device="cuda").to(BF),
+                         (torch.randn(C2, 9 * 64, device="cuda") / 24.0).to(BF), colstats=True)
+    ct = y.shape[3] + C2
+    gm, bt = 1 + 0.2 * torch.randn(ct, device="cuda"), 0.3 * torch.randn(ct, device="cuda")
+    n0 = ops.launch_count()
+    got = ops.groupnorm(y, gm, bt, 32, 1e-5, True, x2=y2)
+    assert ops.launch_count() - n0 == 2                                   # finalize + streaming apply
+    two_pass = ops.groupnorm(y.clone(), gm, bt, 32, 1e-5, True, x2=None if y2 is None else y2.clone())
+    cat = y.float() if y2 is None else torch.cat([y.float(), y2.float()], -1)
+    ref = F.silu(F.group_norm(cat.permute(0, 3, 1, 2), 32, gm, bt, 1e-5)).permute(0, 2, 3, 1)
+    assert rel(got, ref) < 5e-3 and rel(got, two_pass) < 4e-3
+
+
 @pytest.mark.parametrize("B,H,W,C,N", [(2, 16, 16, 64, 64), (3, 9, 7, 128, 96), (1, 32, 32, 640, 640), (14, 8, 8, 320, 320)])
 def test_conv3x3_over_nearest_upsample_folded(ops, B, H, W, C, N):
     """fd_gemm mode 3 (Upsample2D = nearest x2 + conv3x3, …extension.py:661-684 / VAE decoder) == conv3x3 of the materialised

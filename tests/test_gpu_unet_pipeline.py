@@ -22,14 +22,6 @@ def models():
     torch.manual_seed(0)
     cfg = O.TINY_UNET_CONFIG
     ora = O.build_unet(cfg, lq_channels=64, encoder_kwargs=O.TINY_ENCODER_CONFIG)
-    # A trained eps-predictor outputs ~unit-variance noise and its two CFG branches nearly agree.  The random-init net's branches
-    # are unrelated functions of unrelated random embeddings, so guidance 5 amplifies their difference — and the difference of
-    # their independent bf16 rounding errors — fivefold: CFG-combined eps had std 2.0 (oracle/…:record["eps_std_first_tile"]) and
-    # the per-step latent error reached 1.3e-2 at step 20 (profiles/r02_parity_unnormalised_eps.json).  conv_out is scaled so the
-    # combined eps is ~unit variance, as SURVEY §8c's oracle hygiene prescribes; raw eps is still compared separately (relative
-    # errors do not depend on this scale).
-    with torch.no_grad():
-        ora.conv_out.weight.mul_(0.5); ora.conv_out.bias.mul_(0.5)
     # round the oracle's weights through bf16 so both sides hold identical values
     for p in ora.parameters():
         p.data = p.data.to(BF).float()
