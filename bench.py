@@ -473,9 +473,10 @@ def main():
                 (6400.0, "fallback (B200_PROFILING.md)")
             roof_hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_which,
                         "how": "same instrumented pass: algorithmic bytes (bf16 read + write, 4 B/element) of every GroupNorm / LayerNorm "
-                               "call of the UNet evaluation / summed CUDA-event durations (one launch per call)",
+                               "call of the UNet evaluation / summed CUDA-event durations (all launches of a call inside the bracket)",
                         "kernels": {}}
-            for name, kern in (("groupnorm", "gn_fused_kernel"), ("layernorm", "layernorm_kernel")):
+            for name, kern in (("groupnorm", "gn_stats_finalize_kernel + gn_apply_stream_kernel (statistics from the producer's GEMM "
+                                             "epilogue; gn_fused_kernel where a producer leaves none)"), ("layernorm", "layernorm_kernel")):
                 h = r["hbm"].get(name)
                 if h:
                     a = h["bytes"] / h["seconds"] / 1e9

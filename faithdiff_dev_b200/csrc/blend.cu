@@ -67,13 +67,16 @@ __device__ __forceinline__ float euler_step(const BlendParams& p, int t, int ch,
   const long long off = (long long)ly * p.k2 + lx;
   const float eu = load_lowp(p.eps, p.dtype, ((long long)(t * 2 + 0) * p.c + ch) * plane + off);
   const float et = load_lowp(p.eps, p.dtype, ((long long)(t * 2 + 1) * p.c + ch) * plane + off);
-  // noise_pred = eu + g * (et - eu), each op rounded to the tensor dtype (pipeline…:1365)
-  float d = round_lowp(__fsub_rn(et, eu), p.dtype);
-  d = round_lowp(__fmul_rn(d, p.guidance), p.dtype);
-  const float e = round_lowp(__fadd_rn(eu, d), p.dtype);
+  // noise_pred = eu + g * (et - eu), each op rounded to the tensor dtype (pipeline…:1365).  With the latent state kept in fp32
+  // (x_dtype = 2) the guidance arithmetic stays in fp32 as well: its three roundings act on 5x-amplified differences and were the
+  // largest remaining bf16 term of the per-step latent error; it also makes this tail and the N-rank unit form the same arithmetic.
+  const int rd = p.x_dtype == 2 ? 2 : p.dtype;
+  float d = round_lowp(__fsub_rn(et, eu), rd);
+  d = round_lowp(__fmul_rn(d, p.guidance), rd);
+  const float e = round_lowp(__fadd_rn(eu, d), rd);
   // EulerDiscreteScheduler.step (gamma = 0): fp32 sample; sigma*eps rounded to the model dtype
   const float x = load_lowp(p.tiles, p.x_dtype, ((long long)t * p.c + ch) * plane + off);
-  const float se = round_lowp(__fmul_rn(e, p.sigma), p.dtype);
+  const float se = round_lowp(__fmul_rn(e, p.sigma), rd);
   const float pred0 = __fsub_rn(x, se);
   // torch's CUDA true-divide by a host scalar multiplies by the fp32 reciprocal (BinaryDivTrueKernel.cu); the
   // reference runs on CUDA, so that is the arithmetic reproduced here

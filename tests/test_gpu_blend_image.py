@@ -97,14 +97,14 @@ def test_fused_cfg_euler_blend_matches_oracle_scheduler(fd):
         num += part
     c2, _ = ops.canvas_finalize(num, cnt, BF)
     assert (c2 - blended).abs().max() <= 1e-5 * blended.abs().max()
-    # fp32 latent state (the pipeline's default in bf16): the same tail with the oracle's scheduler fed an fp32 sample — diffusers'
-    # step computes in fp32 and casts to the MODEL OUTPUT's dtype (bf16); here the cast is the only thing skipped, so the fp32
-    # canvas equals the blend of the unrounded per-tile updates, next tiles are its exact re-grid, next scaled tiles its bf16 scaling
+    # fp32 latent state (the pipeline's default in bf16): the same tail in fp32 arithmetic on the bf16 eps — CFG combine, Euler
+    # update and blend without any cast to the model dtype: the fp32 canvas equals the blend of the unrounded per-tile updates,
+    # next tiles are its exact re-grid, next scaled tiles its bf16 scaling
     x32 = tiles.float() + 0.001 * torch.randn(tiles.shape, generator=g).cuda()
     new32 = []
     for t in range(T):
         s2 = copy.deepcopy(sch_o)
-        eu, et = eps[t, 0:1], eps[t, 1:2]
+        eu, et = eps[t, 0:1].float(), eps[t, 1:2].float()
         e = eu + 5.0 * (et - eu)
         sg = s2.sigmas[step]                                            # 0-dim host tensor, as in the scheduler
         pred0 = x32[t:t + 1] - sg * e                                   # EulerDiscreteScheduler.step, gamma = 0, before the cast
@@ -112,7 +112,7 @@ def test_fused_cfg_euler_blend_matches_oracle_scheduler(fd):
     blended32 = lo.grids_inverse(torch.cat(new32, 0))
     c32b, clb, ntb, nsb = ops.cfg_euler_blend(eps, x32.contiguous(), la.weights64, la.origins, h, w, 5.0, sigma, sigma_next, next_div)
     assert ntb.dtype == torch.float32 and nsb.dtype == BF and clb.dtype == BF
-    assert (c32b - blended32).abs().max() <= 2e-6 * blended32.abs().max()          # fp32 op order (sigma*eps in bf16 in the kernel)
+    assert (c32b - blended32).abs().max() <= 2e-6 * blended32.abs().max()          # fp32 op order
     assert torch.equal(ntb, lo.grids(c32b)) and torch.equal(clb, c32b.to(BF))
     assert torch.equal(nsb, (ntb * (1.0 / torch.tensor(next_div, dtype=torch.float32).cuda())).to(BF))
 
