@@ -194,37 +194,31 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
         for (int i = 0; i < 128; ++i)
           if (kv0 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
+      // The reference maximum of this block is decided from the row maximum alone; the exponentials then run into REGISTERS (the 128
+      // S values die as the 64 packed P words are born), and only after them does the thread wait for P_{j-1} V_{j-1} — which had the
+      // whole exponential phase to finish — before it rescales O (rarely) and overwrites the single P buffer.  With the wait in front
+      // of the exponentials it was 12 % of a softmax warp's time (profiles/r02_ncu_attention_4096_source.csv).
+      float alpha = 1.f;
+      bool rescale = false;
       if (j == 0) {
         m_used = mx;
       } else {
-        mbar_wait(&bars->o_done, (j - 1) & 1);            // P_{j-1} V_{j-1} finished: sP may be rewritten, O may be rescaled
-        tc_fence_after();
         const bool grew = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, grew)) {
-          const float alpha = fast_exp2((m_used - mx) * p.scale_log2);
-#pragma unroll 1
-          for (int q = 0; q < 4; ++q) {
-            uint32_t o[16];
-            tmem_ld16(t_lane + 128 + q * 16, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(t_lane + 128 + q * 16, o);
-          }
-          tmem_st_wait();
-          l *= alpha;
+        rescale = __any_sync(0xffffffffu, grew);
+        if (rescale) {
+          alpha = fast_exp2((m_used - mx) * p.scale_log2);
           m_used = mx;
         }
       }
       const float nmxs = -m_used * p.scale_log2;
       const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
       uint64_t lsum2 = 0ull;
-      // p = exp2(s*scale - m*scale) -> bf16 -> swizzled smem (scale/subtract and the row sum on packed fp32x2)
+      uint32_t pk[64];
+      // p = exp2(s*scale - m*scale) -> bf16 (scale/subtract and the row sum on packed fp32x2)
       auto exp_block = [&](auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), scale2, nmxs2);
@@ -246,17 +240,38 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
               if (kv0 + c * 32 + i + 1 >= p.lk) a1 = 0.f;
             }
             lsum2 = add_f2(lsum2, pack_f2(a0, a1));
-            pk[i >> 1] = pack_bf16(a0, a1);
-          }
-          uint8_t* half_base = prow + (c >> 1) * kTile;
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int chunk = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) = make_uint4(pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+            pk[c * 16 + (i >> 1)] = pack_bf16(a0, a1);
           }
         }
       };
       if (full) exp_block(std::true_type{}); else exp_block(std::false_type{});
+      if (j > 0) {
+        mbar_wait(&bars->o_done, (j - 1) & 1);            // P_{j-1} V_{j-1} finished: sP may be rewritten, O may be rescaled
+        tc_fence_after();
+        if (rescale) {
+#pragma unroll 1
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[16];
+            tmem_ld16(t_lane + 128 + q * 16, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(t_lane + 128 + q * 16, o);
+          }
+          tmem_st_wait();
+          l *= alpha;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint8_t* half_base = prow + (c >> 1) * kTile;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int chunk = (c & 1) * 4 + g;
+          *reinterpret_cast<uint4*>(half_base + ((chunk ^ sw) << 4)) =
+              make_uint4(pk[c * 16 + g * 4], pk[c * 16 + g * 4 + 1], pk[c * 16 + g * 4 + 2], pk[c * 16 + g * 4 + 3]);
+        }
+      }
       float ls0, ls1;
       unpack_f2(lsum2, ls0, ls1);
       l += ls0 + ls1;
