@@ -58,17 +58,26 @@ __device__ __forceinline__ void exp2_pair_poly(float a0, float a1, float& e0, fl
 }
 
 // kPolyOf8: of every 8 consecutive pairs of a row, the first kPolyOf8 use exp2_pair_poly, the rest MUFU ex2 (0 = all MUFU)
-template <int kPolyOf8>
-__global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+// kKVB = keys per block.  128: two CTAs per SM (256 TMEM columns, 112 KB shared memory each).  64: THREE CTAs per SM (128 TMEM
+// columns, 64 KB, <= 112 registers): a single softmax warp per scheduler keeps the MUFU pipe only 70 % busy next to its FFMA2 /
+// FADD2 / F2FP companions, two reach 93 % (scripts/micro/mufu_rate.cu), and each warp sleeps ~600 cycles per block in barrier /
+// TMEM-load latencies — a third resident warp per scheduler is what keeps two in their exponentials.
+template <int kPolyOf8, int kKVB>
+__global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+  constexpr int kKTile = kKVB * kD * 2;                // one K or V block
+  constexpr int kPH = kKVB / 64;                       // 64-key halves of P
+  constexpr int kCh = kKVB / 32;                       // 32-column chunks of an S row
+  constexpr int kTmemCols = kKVB == 64 ? 128 : 256;
+  constexpr uint32_t kOCol = kKVB;                     // O accumulator behind the S columns
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + kTile;            // 2 stages
-  uint8_t* sV = smem + 3 * kTile;        // 2 stages
-  uint8_t* sP = smem + 5 * kTile;        // 2 halves (64 keys each)
-  AttnBars* bars = reinterpret_cast<AttnBars*>(smem + 7 * kTile);
+  uint8_t* sK = smem + kTile;                          // 2 stages
+  uint8_t* sV = sK + 2 * kKTile;                       // 2 stages
+  uint8_t* sP = sV + 2 * kKTile;                       // kPH halves (64 keys each)
+  AttnBars* bars = reinterpret_cast<AttnBars*>(sP + kPH * kTile);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qblk = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
-  const int nkv = (p.lk + kKV - 1) / kKV;
+  const int nkv = (p.lk + kKVB - 1) / kKVB;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.qmap); tma_prefetch_desc(&p.kmap); tma_prefetch_desc(&p.vmap);
@@ -84,7 +93,7 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, 256);
+    tmem_alloc(&bars->tmem_base, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -101,14 +110,14 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
       auto load_k = [&](int j) {
         const int s = j & 1;
         mbar_wait(&bars->k_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->k_full[s], kTile);
-        tma_load_2d(&p.kmap, &bars->k_full[s], sK + s * kTile, head * kD, b * p.lk + j * kKV);
+        mbar_arrive_expect_tx(&bars->k_full[s], kKTile);
+        tma_load_2d(&p.kmap, &bars->k_full[s], sK + s * kKTile, head * kD, b * p.lk + j * kKVB);
       };
       auto load_v = [&](int j) {
         const int s = j & 1;
         mbar_wait(&bars->v_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&bars->v_full[s], kTile);
-        tma_load_2d(&p.vmap, &bars->v_full[s], sV + s * kTile, head * kD, b * p.lk + j * kKV);
+        mbar_arrive_expect_tx(&bars->v_full[s], kKTile);
+        tma_load_2d(&p.vmap, &bars->v_full[s], sV + s * kKTile, head * kD, b * p.lk + j * kKVB);
       };
       // request order = order in which the slots become free: K_{j+1}'s slot (after S_{j-1}) before V_j's (after PV_{j-2})
       load_k(0);
@@ -121,11 +130,11 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc(128, 128, 1, 0, 0);
+      const uint32_t idesc_s = umma_idesc(128, kKVB, 1, 0, 0);
       const uint32_t idesc_o = umma_idesc(128, 64, 1, 0, 1);   // B (=V) is MN-major
       const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP);
       auto issue_s = [&](int j) {
-        const uint32_t aK = smem_u32(sK + (j & 1) * kTile);
+        const uint32_t aK = smem_u32(sK + (j & 1) * kKTile);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_f16(tmem, umma_desc_sw128(aQ + k * 32, 16, 1024), umma_desc_sw128(aK + k * 32, 16, 1024), idesc_s, k != 0);
@@ -148,10 +157,10 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
         mbar_wait(&bars->v_full[s], (j >> 1) & 1);
         mbar_wait(&bars->p_full, j & 1);
         tc_fence_after();
-        const uint32_t aV = smem_u32(sV + s * kTile);
+        const uint32_t aV = smem_u32(sV + s * kKTile);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_f16(tmem + 128, umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+        for (int k = 0; k < kKVB / 16; ++k)
+          umma_f16(tmem + kOCol, umma_desc_sw128(aP + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                    umma_desc_sw128(aV + k * 2048, 0, 1024), idesc_o, (j != 0) || (k != 0));
         tc_commit(&bars->v_empty[s]);
         tc_commit(&bars->o_done);
@@ -168,21 +177,21 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
-      uint32_t v[128];
+      uint32_t v[kKVB];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(t_lane + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
+      for (int c = 0; c < kCh; ++c) tmem_ld32(t_lane + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_read);          // the tensor core may now compute S_{j+1}
-      const int kv0 = j * kKV;
-      const bool full = kv0 + kKV <= p.lk;               // only the last block can need masking (warp-uniform)
+      const int kv0 = j * kKVB;
+      const bool full = kv0 + kKVB <= p.lk;               // only the last block can need masking (warp-uniform)
       float mx = m_used;
       if (full) {
         // four independent 3-input-max chains (a single chain is 64 dependent instructions of latency)
         float m1 = mx, m2 = mx, m3 = mx;
 #pragma unroll
-        for (int i = 0; i < 128; i += 8) {
+        for (int i = 0; i < kKVB; i += 8) {
           mx = max3_f(mx, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
           m1 = max3_f(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
           m2 = max3_f(m2, __uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
@@ -191,7 +200,7 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
         mx = fmaxf(max3_f(mx, m1, m2), m3);
       } else {
 #pragma unroll
-        for (int i = 0; i < 128; ++i)
+        for (int i = 0; i < kKVB; ++i)
           if (kv0 + i < p.lk) mx = fmaxf(mx, __uint_as_float(v[i]));
       }
       // The reference maximum of this block is decided from the row maximum alone; the exponentials then run into REGISTERS (the 128
@@ -213,12 +222,12 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
       const float nmxs = -m_used * p.scale_log2;
       const uint64_t nmxs2 = pack_f2(nmxs, nmxs);
       uint64_t lsum2 = 0ull;
-      uint32_t pk[64];
+      uint32_t pk[kKVB / 2];
       // p = exp2(s*scale - m*scale) -> bf16 (scale/subtract and the row sum on packed fp32x2)
       auto exp_block = [&](auto full_tag) {
         constexpr bool kFull = decltype(full_tag)::value;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kCh; ++c) {
 #pragma unroll
           for (int i = 0; i < 32; i += 2) {
             const uint64_t t = fma_f2(pack_f2(__uint_as_float(v[c * 32 + i]), __uint_as_float(v[c * 32 + i + 1])), scale2, nmxs2);
@@ -252,18 +261,18 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {
             uint32_t o[16];
-            tmem_ld16(t_lane + 128 + q * 16, o);
+            tmem_ld16(t_lane + kOCol + q * 16, o);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(t_lane + 128 + q * 16, o);
+            tmem_st16(t_lane + kOCol + q * 16, o);
           }
           tmem_st_wait();
           l *= alpha;
         }
       }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < kCh; ++c) {
         uint8_t* half_base = prow + (c >> 1) * kTile;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -288,7 +297,7 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
-      tmem_ld32(t_lane + 128 + c * 32, o);
+      tmem_ld32(t_lane + kOCol + c * 32, o);
       tmem_ld_wait();
       if (qi < p.lq) {
 #pragma unroll
@@ -308,7 +317,7 @@ __global__ void __launch_bounds__(192, 2) attention_d64_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 256);
+    tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -559,14 +568,27 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
   p.out = (__nv_bfloat16*)out; p.ldo = ldo; p.lq = lq; p.lk = lk; p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.causal = causal;
-  const size_t smem_bytes = 7 * kTile + sizeof(AttnBars);
+  const size_t smem_bytes = 7 * kTile + sizeof(AttnBars);                    // 128-key blocks: Q + 2 K + 2 V + 2 P halves
+  const size_t smem_kv64 = 4 * kTile + sizeof(AttnBars);                     // 64-key blocks: Q + 2 K/2 + 2 V/2 + 1 P half
   const size_t smem_short = 7 * kTile + sizeof(AttnShortBars);
+  static int kv64 = -1;
+  if (kv64 < 0) { const char* e = getenv("FD_ATTN_KV64"); kv64 = e ? atoi(e) : 1; }
+  const bool use64 = kv64 && lk > kKV;
+  if (use64) {            // K / V boxes of 64 keys
+    for (int i = 1; i < 3; ++i) {
+      uint64_t dims[2] = {(uint64_t)heads * kD, (uint64_t)rows[i]};
+      uint64_t str[1] = {(uint64_t)ld[i] * 2};
+      uint32_t box[2] = {kD, 64};
+      if (encode_tensor_map(maps[i], ptr[i], 2, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_128B)) return 3;
+    }
+  }
   static bool attr = false;
   if (!attr) {
-    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<0, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<3, 128>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<0, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv64));
+    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<2, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv64));
+    FD_CHECK_CUDA(cudaFuncSetAttribute((attention_d64_kernel<3, 64>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv64));
     FD_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_shortkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_short));
     attr = true;
   }
@@ -588,13 +610,15 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
     FD_CHECK_CUDA(launch_pdl(attention_d64_shortkv_kernel, grid, dim3(192), smem_short, stream, 1, p));
   } else {
     dim3 grid(nqb, heads, batch);
-    // FD_ATTN_POLY = 2 / 3 / 4: that many of every 8 exponential pairs on the FMA pipe (opt-in; measured: 3 gives +2 % at 4096 keys)
+    // FD_ATTN_POLY = 2 / 3: that many of every 8 exponential pairs on the FMA pipe (opt-in); FD_ATTN_KV64=0: 128-key blocks, 2 CTAs / SM
     static int poly = -1;
     if (poly < 0) { const char* e = getenv("FD_ATTN_POLY"); poly = e ? atoi(e) : 0; }
-    if (poly == 2) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<2>, grid, dim3(192), smem_bytes, stream, 1, p));
-    else if (poly == 3) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<3>, grid, dim3(192), smem_bytes, stream, 1, p));
-    else if (poly == 4) FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<4>, grid, dim3(192), smem_bytes, stream, 1, p));
-    else FD_CHECK_CUDA(launch_pdl(attention_d64_kernel<0>, grid, dim3(192), smem_bytes, stream, 1, p));
+    if (use64) {
+      if (poly == 2) FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<2, 64>), grid, dim3(192), smem_kv64, stream, 1, p));
+      else if (poly == 3) FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<3, 64>), grid, dim3(192), smem_kv64, stream, 1, p));
+      else FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<0, 64>), grid, dim3(192), smem_kv64, stream, 1, p));
+    } else if (poly == 3) FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<3, 128>), grid, dim3(192), smem_bytes, stream, 1, p));
+    else FD_CHECK_CUDA(launch_pdl((attention_d64_kernel<0, 128>), grid, dim3(192), smem_bytes, stream, 1, p));
   }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
