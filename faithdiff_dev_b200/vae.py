@@ -83,6 +83,43 @@ def _down8(n):
     return n
 
 
+class StageGraphs:
+    """CUDA graphs for the one-time tiled stages: one graph per (network, batch shape), static input / output buffers, all graphs
+    in ONE shared memory pool (they never replay concurrently, so their intermediates alias).  At N = 8 a rank runs only two LQ-
+    encoder tiles but still ~1000 launches for them: eager, the stage was bound by the host's launch rate (encode 60 ms against
+    27 ms of GPU work); replayed, it is one launch.  FD_STAGE_GRAPHS=0 keeps the eager path."""
+
+    def __init__(self):
+        import os
+        self.enabled = os.environ.get("FD_STAGE_GRAPHS", "1") == "1"
+        self.pool = None
+
+    def __call__(self, fn, x):
+        owner = getattr(fn, "__self__", None)        # graphs live ON the network object: they die with its weights
+        if not self.enabled or owner is None or torch.cuda.is_current_stream_capturing():
+            return fn(x)
+        cache = owner.__dict__.setdefault("_stage_graphs", {})
+        key = (fn.__name__, tuple(x.shape), x.dtype)
+        ent = cache.get(key)
+        if ent is None:
+            xin = x.clone()
+            fn(xin)                                   # eager warm-up: kernel attributes, persistent sync words, allocator pools
+            torch.cuda.current_stream().synchronize()
+            if self.pool is None:
+                self.pool = torch.cuda.graph_pool_handle()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self.pool):
+                out = fn(xin)
+            ent = cache[key] = (g, xin, out)
+        g, xin, out = ent
+        xin.copy_(x)
+        g.replay()
+        return out.clone()                            # the static output is overwritten by the next replay
+
+
+STAGE_GRAPHS = StageGraphs()
+
+
 # tiles of one shape are pushed through the network together (batch axis): the tiled stages are hundreds of small
 # launches per tile — at 45 VAE tiles per 4K image the per-launch latency, not the arithmetic, was their cost
 TILE_BATCH = 8
@@ -111,7 +148,7 @@ def _tiled(x, fn, tile_in, stride, blend_extent, row_limit, out_shape=None, dist
     for items in mine.values():
         for k in range(0, len(items), TILE_BATCH):
             chunk = items[k:k + TILE_BATCH]
-            out = fn(torch.cat([src for _, src in chunk], dim=0) if len(chunk) > 1 else chunk[0][1].contiguous())
+            out = STAGE_GRAPHS(fn, torch.cat([src for _, src in chunk], dim=0) if len(chunk) > 1 else chunk[0][1].contiguous())
             for t, (idx, _) in enumerate(chunk):
                 tiles[idx] = out[t * bx:(t + 1) * bx]
     if shard:
@@ -159,6 +196,7 @@ class Encoder:
         self.dtype = BF16
 
     def load_state_dict(self, sd, strict=True, device="cuda"):
+        self.__dict__.pop("_stage_graphs", None)      # captured graphs hold the old weights' addresses
         W = Weights(sd, torch.device(device))
         self.device = torch.device(device)
         self.conv_in = (W.conv3("conv_in.weight"), W.f32("conv_in.bias"))
@@ -249,6 +287,7 @@ class AutoencoderKL:
         self.use_tiling = False
 
     def load_state_dict(self, sd, strict=True, device="cuda"):
+        self.__dict__.pop("_stage_graphs", None)      # captured graphs hold the old weights' addresses
         dev = torch.device(device)
         self.device = dev
         g = self.config.norm_num_groups
