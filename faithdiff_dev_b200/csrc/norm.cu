@@ -763,9 +763,26 @@ extern "C" int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x
   // L2 budget for the re-read: ~56 MB of the 126 MB (both dies hold a copy of far lines; the output stream needs room too)
   const double tensor_bytes = (double)batch * hw * ct * 2.0;
   const float keep_frac = !l2hint ? -1.f : (tensor_bytes <= 56e6 ? 1.f : (float)(56e6 / tensor_bytes));
-  gn_fused_kernel<<<dim3(cps * batch), dim3(threads), smem, stream>>>(
-      (const __nv_bfloat16*)x0, c0, (const __nv_bfloat16*)x1, c1, (long long)hw, groups, R, eps, gamma, beta, (int)silu,
-      (__nv_bfloat16*)out, partial, (unsigned*)sync, batch, cps, keep_frac);
+  // Cooperative launch: the kernel's per-sample arrive / wait needs every CTA of the grid resident at once.  The grid is sized from
+  // the occupancy API, but only a cooperative launch makes the runtime CHECK that (a changed carve-out, MPS, a profiler replay):
+  // if it refuses, the three-launch path runs instead of a kernel that could spin until its 2 s trap.
+  {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cps * batch); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const __nv_bfloat16*)x0, (int)c0, (const __nv_bfloat16*)x1, (int)c1,
+                                             (long long)hw, (int)groups, R, eps, gamma, beta, (int)silu, (__nv_bfloat16*)out, partial,
+                                             (unsigned*)sync, (int)batch, cps, keep_frac);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported || e == cudaErrorLaunchOutOfResources) {
+      cudaGetLastError();
+      return fd_groupnorm_nhwc(x0, c0, x1, c1, gamma, beta, out, batch, hw, groups, eps, silu, work, stream_);
+    }
+    FD_CHECK_CUDA(e);
+  }
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
