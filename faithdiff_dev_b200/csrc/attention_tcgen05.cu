@@ -58,6 +58,13 @@ __device__ __forceinline__ void exp2_pair_poly(float a0, float a1, float& e0, fl
 }
 
 // kPolyOf8: of every 8 consecutive pairs of a row, the first kPolyOf8 use exp2_pair_poly, the rest MUFU ex2 (0 = all MUFU)
+#ifdef FD_ATTN_TRACE
+// development only (scripts/dev_attn_trace.py): clock64 stamps of one CTA's first softmax warp and of its MMA thread, key blocks 16..31
+__device__ long long g_attn_trace[16][12];
+#define FD_TR(k) do { if (blockIdx.x == 5 && blockIdx.y == 1 && blockIdx.z == 2 && lane == 0 && j >= 16 && j < 32) g_attn_trace[j - 16][k] = clock64(); } while (0)
+#else
+#define FD_TR(k) do { } while (0)
+#endif
 // kKVB = keys per block.  128: two CTAs per SM (256 TMEM columns, 112 KB shared memory each).  64: THREE CTAs per SM (128 TMEM
 // columns, 64 KB, <= 112 registers): a single softmax warp per scheduler keeps the MUFU pipe only 70 % busy next to its FFMA2 /
 // FADD2 / F2FP companions, two reach 93 % (scripts/micro/mufu_rate.cu), and each warp sleeps ~600 cycles per block in barrier /
@@ -151,12 +158,15 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
           mbar_wait(&bars->k_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
           mbar_wait(&bars->s_read, j & 1);
           tc_fence_after();
+          FD_TR(8);
           issue_s(j + 1);
+          FD_TR(9);
         }
         const int s = j & 1;
         mbar_wait(&bars->v_full[s], (j >> 1) & 1);
         mbar_wait(&bars->p_full, j & 1);
         tc_fence_after();
+        FD_TR(10);
         const uint32_t aV = smem_u32(sV + s * kKTile);
 #pragma unroll
         for (int k = 0; k < kKVB / 16; ++k)
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
                    umma_desc_sw128(aV + k * 2048, 0, 1024), idesc_o, (j != 0) || (k != 0));
         tc_commit(&bars->v_empty[s]);
         tc_commit(&bars->o_done);
+        FD_TR(11);
       }
     }
   } else {
@@ -175,8 +186,10 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
     const int sw = r & 7;
     const uint64_t scale2 = pack_f2(p.scale_log2, p.scale_log2);
     for (int j = 0; j < nkv; ++j) {
+      if (warp == 2) FD_TR(0);
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
+      if (warp == 2) FD_TR(1);
       uint32_t v[kKVB];
 #pragma unroll
       for (int c = 0; c < kCh; ++c) tmem_ld32(t_lane + c * 32, reinterpret_cast<uint32_t(&)[32]>(v[c * 32]));
@@ -184,6 +197,7 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->s_read);          // the tensor core may now compute S_{j+1}
+      if (warp == 2) FD_TR(2);
       const int kv0 = j * kKVB;
       const bool full = kv0 + kKVB <= p.lk;               // only the last block can need masking (warp-uniform)
       float mx = m_used;
@@ -207,6 +221,7 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
       // S values die as the 64 packed P words are born), and only after them does the thread wait for P_{j-1} V_{j-1} — which had the
       // whole exponential phase to finish — before it rescales O (rarely) and overwrites the single P buffer.  With the wait in front
       // of the exponentials it was 12 % of a softmax warp's time (profiles/r02_ncu_attention_4096_source.csv).
+      if (warp == 2) FD_TR(3);
       float alpha = 1.f;
       bool rescale = false;
       if (j == 0) {
@@ -254,9 +269,11 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
         }
       };
       if (full) exp_block(std::true_type{}); else exp_block(std::false_type{});
+      if (warp == 2) FD_TR(4);
       if (j > 0) {
         mbar_wait(&bars->o_done, (j - 1) & 1);            // P_{j-1} V_{j-1} finished: sP may be rewritten, O may be rescaled
         tc_fence_after();
+        if (warp == 2) FD_TR(5);
         if (rescale) {
 #pragma unroll 1
           for (int q = 0; q < 4; ++q) {
@@ -288,6 +305,7 @@ __global__ void __launch_bounds__(192, kKVB == 64 ? 3 : 2) attention_d64_kernel(
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars->p_full);
+      if (warp == 2) FD_TR(6);
     }
     mbar_wait(&bars->o_done, (nkv - 1) & 1);
     tc_fence_after();
@@ -624,6 +642,13 @@ static int attention_d64_impl(const void* q, int64_t ldq, const void* k, int64_t
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#ifdef FD_ATTN_TRACE
+extern "C" int fd_debug_read_attn_trace(long long* host_out) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host_out, fd::g_attn_trace, sizeof(long long) * 16 * 12);
+}
+#endif
 
 extern "C" int fd_attention_d64(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* out,
                                 int64_t ldo, int32_t batch, int32_t heads, int32_t lq, int32_t lk, float scale, void* stream) {
