@@ -111,7 +111,7 @@ def test_conv3x3_channel_slice_views(ops, cin, cout, act, alpha, res):
 @pytest.mark.timeout(120)
 @pytest.mark.parametrize("B,heads,lq,lk", [(2, 2, 256, 256), (2, 10, 4096, 4096), (2, 4, 1024, 77), (1, 1, 16, 16), (2, 3, 200, 333),
                                            (3, 20, 1000, 77), (1, 2, 2048, 128), (2, 3, 512, 384), (1, 2, 256, 640), (3, 5, 1024, 1024),
-                                           (1, 1, 256, 1920), (2, 2, 384, 512)])
+                                           (1, 1, 256, 1920), (2, 2, 384, 512), (1, 2, 100, 130), (2, 1, 128, 192), (1, 3, 640, 200)])
 def test_attention_d64(ops, B, heads, lq, lk):
     torch.manual_seed(3)
     C = heads * 64
