@@ -26,3 +26,7 @@ timeout 200 python scripts/dev_attn512.py > gpurun_out/r02_attn512.log 2>&1; ech
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:attention_d512_kernel --launch-skip 4 -c 1 -o gpurun_out/r02_attn512 \
   python scripts/dev_attn512.py > gpurun_out/r02_attn512_ncu.log 2>&1; echo "ncu attn512 rc=$?"
 ncu -i gpurun_out/r02_attn512.ncu-rep --page raw --csv > gpurun_out/r02_ncu_attention_d512_raw.csv 2>/dev/null
+# 6. GroupNorm from producer statistics (finalize + streaming apply) at the tile-step's largest shape, L2 flushed
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:gn_apply_stream_kernel --launch-skip 6 -c 1 -o gpurun_out/r02_gn_apply \
+  python scripts/dev_norm_bench.py gns > gpurun_out/r02_gn_apply_ncu.log 2>&1; echo "ncu gn apply rc=$?"
+ncu -i gpurun_out/r02_gn_apply.ncu-rep --page raw --csv > gpurun_out/r02_ncu_gn_apply_raw.csv 2>/dev/null
