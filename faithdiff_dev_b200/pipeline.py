@@ -375,10 +375,11 @@ class FaithDiffStableDiffusionXLPipeline:
         # (keyed on the IDENTITY + version counter of the caller's embedding tensors; the cache keeps them referenced, so their
         # storage cannot be recycled for different data)
         old = getattr(self, "_kv_src", None)
-        kv_fresh = (kv_src is None or old is None or getattr(self, "_kv_unet", None) is not unet
+        wver = (unet, getattr(unet, "_weights_version", 0))       # compared by identity (the class defines no __eq__) + version
+        kv_fresh = (kv_src is None or old is None or getattr(self, "_kv_unet", None) != wver
                     or any(a is not b for a, b in zip(kv_src, old[0])) or tuple(t._version for t in kv_src) != old[1])
         if kv_fresh:
-            self._kv_val, self._kv_unet = unet.text_kv(pe), unet
+            self._kv_val, self._kv_unet = unet.text_kv(pe), wver
             self._kv_src = None if kv_src is None else (kv_src, tuple(t._version for t in kv_src))
         kv, lk = self._kv_val
         # work units = (tile, CFG branch); contiguous balanced ranges per rank (a whole CFG pair per launch slot on 1 GPU)
@@ -400,7 +401,7 @@ class FaithDiffStableDiffusionXLPipeline:
                       for g in plan_launch_groups(list(range(T)), range(1, max(1, self.tiles_per_launch) + 1))]
         else:
             groups = plan_unit_groups(my_units, 2 * max(1, self.tiles_per_launch))
-        gbase = (k1, k2, bool(add_sample), lk, self.use_cuda_graph)
+        gbase = (k1, k2, bool(add_sample), lk, self.use_cuda_graph, wver)     # captured graphs hold the weights' addresses
         if self._graphs.get("key") != gbase:
             self._graphs = {"key": gbase}
         plans = []

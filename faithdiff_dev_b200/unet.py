@@ -193,6 +193,7 @@ class UNet2DConditionModel:
                 raise RuntimeError("unexpected keys in state_dict: %s…" % missing[:5])
         self._loaded = True
         self._kv_cache = (None, None, None)
+        self._weights_version = getattr(self, "_weights_version", 0) + 1     # pipelines key their graphs / text K/V caches on it
         return self
 
     # ------------------------------------------------------------------ pieces
