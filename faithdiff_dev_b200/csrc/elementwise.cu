@@ -36,7 +36,7 @@ __global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, __nv_bfloat16* __r
   }
 }
 template <typename TO>
-__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, TO* __restrict__ out, int c, long long hw) {
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, TO* __restrict__ out, int c, long long hw, long long ldc) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -44,7 +44,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, TO* __r
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const long long p = p0 + i;
     const int cc = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (cc < c && p < hw) ? __bfloat162float(x[((long long)b * hw + p) * c + cc]) : 0.f;
+    tile[i][threadIdx.x] = (cc < c && p < hw) ? __bfloat162float(x[((long long)b * hw + p) * ldc + cc]) : 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -421,16 +421,21 @@ extern "C" int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out, int32
   return 0;
 }
 
-extern "C" int fd_nhwc_to_nchw(const void* x, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream_) {
+extern "C" int fd_nhwc_to_nchw_strided(const void* x, int64_t ldc, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw,
+                                       void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(x && out && out_dtype >= 0 && out_dtype <= 2, "fd_nhwc_to_nchw: bad arguments");
+  FD_REQUIRE(x && out && out_dtype >= 0 && out_dtype <= 2 && ldc >= c, "fd_nhwc_to_nchw: bad arguments");
   dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, batch), block(32, 8);
-  if (out_dtype == 0) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, c, hw);
-  else if (out_dtype == 1) nhwc_to_nchw_kernel<__half><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__half*)out, c, hw);
-  else nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (float*)out, c, hw);
+  if (out_dtype == 0) nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, c, hw, ldc);
+  else if (out_dtype == 1) nhwc_to_nchw_kernel<__half><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__half*)out, c, hw, ldc);
+  else nhwc_to_nchw_kernel<float><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (float*)out, c, hw, ldc);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fd_nhwc_to_nchw(const void* x, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream_) {
+  return fd_nhwc_to_nchw_strided(x, c, out, out_dtype, batch, c, hw, stream_);
 }
 
 extern "C" int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch, int32_t h, int32_t w, int32_t oh, int32_t ow,

@@ -172,6 +172,10 @@ int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch, int32_t h,
  * out_dtype: 0 bf16, 1 fp16, 2 fp32.                                                                       */
 int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out_bf16, int32_t batch, int32_t c, int64_t hw, void* stream);
 int fd_nhwc_to_nchw(const void* x_bf16, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream);
+/* same from a channel-padded NHWC buffer: pixels ldc elements apart, the first c channels are emitted (the tensor-core path of the
+ * few-output-channel convs — UNet conv_out 320 -> 4, VAE decoder conv_out 128 -> 3 — computes 32 padded channels)              */
+int fd_nhwc_to_nchw_strided(const void* x_nhwc_bf16, int64_t ldc, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw,
+                            void* stream);
 /* direct 3x3 convs (pad 1) with a tiny channel count on one side (conv_in 4→C, conv_out C→4, VAE 3→128 / 128→3):
  * w bf16 [cout, 9*cin] (tap-major).  cin <= 8: x per in_mode (0 NHWC bf16, 1 NCHW bf16, 2 NCHW fp32, 3 NCHW fp16),
  * out NHWC bf16 (out_mode 0).  cout <= 8: x NHWC bf16 (in_mode 0), out per out_mode (0 NHWC bf16, 1 NCHW bf16,

@@ -299,6 +299,24 @@ def test_layernorm(ops, rows, cols):
     assert rel(ops.layernorm(x, g, b, 1e-5), F.layer_norm(x.float(), (cols,), g, b, 1e-5)) < 5e-3
 
 
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 256, 256, 64, 4), (1, 300, 260, 128, 3), (14, 128, 128, 320, 4)])
+def test_small_cout_conv_on_tensor_cores(ops, monkeypatch, B, H, W, cin, cout):
+    """conv_out of the UNet (320 -> 4) / VAE decoder (128 -> 3) at sizes that take the tensor-core path (weights zero-padded to 32
+    output channels + strided NHWC -> NCHW pass) == torch == the direct warp-per-pixel kernel."""
+    torch.manual_seed(cin + cout)
+    y = torch.randn(B, H, W, cin, device="cuda").to(BF)
+    w = (torch.randn(cout, cin, 3, 3, device="cuda") / (9 * cin) ** 0.5).to(BF)
+    b = torch.randn(cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    n0 = ops.launch_count()
+    out = ops.conv3x3_small_out(y, wp, b, out_dtype=BF)
+    assert ops.launch_count() - n0 == 2 and out.shape == (B, cout, H, W) and out.is_contiguous()
+    monkeypatch.setenv("FD_SMALLCOUT_TC", "0")
+    direct = ops.conv3x3_small_out(y, wp, b, out_dtype=BF)
+    ref = F.conv2d(y.permute(0, 3, 1, 2).float(), w.float(), b, padding=1)
+    assert rel(out, ref) < 5e-3 and rel(direct, ref) < 5e-3
+
+
 def test_small_convs_and_layouts(ops):
     torch.manual_seed(6)
     x = torch.randn(2, 4, 20, 28, device="cuda").to(BF)
