@@ -65,6 +65,7 @@ _SIGS = {
     "fd_axpby_bf16": [vp, i64, vp, i64, vp, i64, i64, i32, f32, f32, vp],
     "fd_upsample_nearest_nhwc": [vp, vp, i32, i32, i32, i32, i32, i32, vp],
     "fd_nchw_to_nhwc": [vp, i32, vp, i32, i32, i64, vp],
+    "fd_nchw_to_nhwc_padded": [vp, i32, vp, i32, i32, i32, i64, vp],
     "fd_nhwc_to_nchw": [vp, vp, i32, i32, i32, i64, vp],
     "fd_nhwc_to_nchw_strided": [vp, i64, vp, i32, i32, i32, i64, vp],
     "fd_conv3x3_small": [vp, i32, vp, vp, vp, i32, i64, i32, i32, i32, i32, i32, vp],

@@ -18,7 +18,7 @@ template <> __device__ __forceinline__ float from_f<float>(float v) { return v; 
 
 // ------------------------------------------------------------------ NCHW <-> NHWC (32x32 smem transpose tiles)
 template <typename TI>
-__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, long long hw) {
+__global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, long long hw, int ldc) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -32,7 +32,7 @@ __global__ void nchw_to_nhwc_kernel(const TI* __restrict__ x, __nv_bfloat16* __r
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const long long p = p0 + i;
     const int cc = c0 + threadIdx.x;
-    if (cc < c && p < hw) out[((long long)b * hw + p) * c + cc] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (cc < ldc && p < hw) out[((long long)b * hw + p) * ldc + cc] = __float2bfloat16_rn(tile[threadIdx.x][i]);   // channels [c, ldc) = 0
   }
 }
 template <typename TO>
@@ -409,16 +409,21 @@ static inline unsigned grid_for(long long total, int threads, int per_sm = 16) {
   return (unsigned)blocks;
 }
 
-extern "C" int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out, int32_t batch, int32_t c, int64_t hw, void* stream_) {
+extern "C" int fd_nchw_to_nhwc_padded(const void* x, int32_t in_dtype, void* out, int32_t batch, int32_t c, int32_t ldc, int64_t hw,
+                                      void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  FD_REQUIRE(x && out && in_dtype >= 0 && in_dtype <= 2, "fd_nchw_to_nhwc: bad arguments");
-  dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, batch), block(32, 8);
-  if (in_dtype == 0) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, c, hw);
-  else if (in_dtype == 1) nchw_to_nhwc_kernel<__half><<<grid, block, 0, stream>>>((const __half*)x, (__nv_bfloat16*)out, c, hw);
-  else nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>((const float*)x, (__nv_bfloat16*)out, c, hw);
+  FD_REQUIRE(x && out && in_dtype >= 0 && in_dtype <= 2 && ldc >= c, "fd_nchw_to_nhwc: bad arguments");
+  dim3 grid((unsigned)((hw + 31) / 32), (ldc + 31) / 32, batch), block(32, 8);
+  if (in_dtype == 0) nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, c, hw, ldc);
+  else if (in_dtype == 1) nchw_to_nhwc_kernel<__half><<<grid, block, 0, stream>>>((const __half*)x, (__nv_bfloat16*)out, c, hw, ldc);
+  else nchw_to_nhwc_kernel<float><<<grid, block, 0, stream>>>((const float*)x, (__nv_bfloat16*)out, c, hw, ldc);
   ++g_launches;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+extern "C" int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out, int32_t batch, int32_t c, int64_t hw, void* stream_) {
+  return fd_nchw_to_nhwc_padded(x, in_dtype, out, batch, c, c, hw, stream_);
 }
 
 extern "C" int fd_nhwc_to_nchw_strided(const void* x, int64_t ldc, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw,

@@ -56,11 +56,17 @@ class _StemBlock:
         self.wfc, self.bfc = W.mat("mlp.c_fc.weight"), W.f32("mlp.c_fc.bias")
         self.wpr, self.bpr = W.mat("mlp.c_proj.weight"), W.f32("mlp.c_proj.bias")
         self.E = self.wout.shape[0]
+        self.win_v, self.bin_v = self.win[2 * self.E:].contiguous(), self.bin[2 * self.E:].contiguous()
 
     def __call__(self, x, groups, seq, hw):
         y = ops.layernorm(x, *self.ln1)
-        qkv = ops.gemm(y, self.win, bias=self.bin)
-        a = ops.batch_axis_attention(qkv, groups, seq, hw, self.E, self.heads)
+        if seq == 1:
+            # one element on the attended (batch) axis — the tile-step evaluates the stem once per tile because its CFG halves are
+            # identical: the softmax is exactly 1 and the attention output is V, so only the V third of in_proj is computed
+            a = ops.gemm(y, self.win_v, bias=self.bin_v)
+        else:
+            qkv = ops.gemm(y, self.win, bias=self.bin)
+            a = ops.batch_axis_attention(qkv, groups, seq, hw, self.E, self.heads)
         x = ops.gemm(a, self.wout, bias=self.bout, residual=x)
         y = ops.layernorm(x, *self.ln2)
         h = ops.gemm(y, self.wfc, bias=self.bfc, act=3)

@@ -171,6 +171,10 @@ int fd_upsample_nearest_nhwc(const void* x, void* out, int32_t batch, int32_t h,
 /* NCHW <-> NHWC layout changes at the module boundary (the reference's forward signatures are NCHW). in_dtype /
  * out_dtype: 0 bf16, 1 fp16, 2 fp32.                                                                       */
 int fd_nchw_to_nhwc(const void* x, int32_t in_dtype, void* out_bf16, int32_t batch, int32_t c, int64_t hw, void* stream);
+/* same with the channel axis zero-padded to ldc (the UNet's conv_in, 4 -> 320 channels, runs on the tensor cores over an
+ * 8-channel NHWC image: one 64-wide K block per tap, zero-filled past channel 8)                                              */
+int fd_nchw_to_nhwc_padded(const void* x, int32_t in_dtype, void* out_bf16, int32_t batch, int32_t c, int32_t ldc, int64_t hw,
+                           void* stream);
 int fd_nhwc_to_nchw(const void* x_bf16, void* out, int32_t out_dtype, int32_t batch, int32_t c, int64_t hw, void* stream);
 /* same from a channel-padded NHWC buffer: pixels ldc elements apart, the first c channels are emitted (the tensor-core path of the
  * few-output-channel convs — UNet conv_out 320 -> 4, VAE decoder conv_out 128 -> 3 — computes 32 padded channels)              */

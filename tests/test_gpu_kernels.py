@@ -356,6 +356,36 @@ def test_embeddings_and_small_linear(ops):
     assert rel(out, F.silu(F.silu(x) @ w.float().t() + b) + add) < 1e-4
 
 
+def test_batch_axis_attention_of_one_element_is_the_v_projection(ops):
+    """The tile-step evaluates the FaithDiff stem once per tile (its CFG halves are identical), so nn.MultiheadAttention over the
+    batch axis (…extension.py:238-260, batch_first=False) sees ONE element: softmax = 1, output = V.  The V third of in_proj alone
+    must equal the full in_proj + batch-axis attention kernel bit for bit."""
+    torch.manual_seed(12)
+    E, heads, groups, hw = 640, 8, 3, 1024
+    y = torch.randn(groups * hw, E, device="cuda").to(BF)
+    win = (torch.randn(3 * E, E, device="cuda") / E ** 0.5).to(BF)
+    bin_ = torch.randn(3 * E, device="cuda") * 0.1
+    full = ops.batch_axis_attention(ops.gemm(y, win, bias=bin_), groups, 1, hw, E, heads)
+    v_only = ops.gemm(y, win[2 * E:].contiguous(), bias=bin_[2 * E:].contiguous())
+    assert torch.equal(full, v_only)
+
+
+@pytest.mark.parametrize("B,H,W,cout", [(14, 128, 128, 320), (2, 200, 180, 64)])
+def test_small_cin_conv_on_tensor_cores(ops, monkeypatch, B, H, W, cout):
+    """The UNet's conv_in (4 -> 320, NCHW in, NHWC out into a channel-slice view) on the tensor cores == the direct kernel == torch."""
+    torch.manual_seed(cout)
+    x = torch.randn(B, 4, H, W, device="cuda").to(BF)
+    w = (torch.randn(cout, 4, 3, 3, device="cuda") / 6).to(BF)
+    b = torch.randn(cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    buf = torch.zeros(B, H, W, 2 * cout, device="cuda", dtype=BF)
+    ops.conv3x3_small_in(x, wp, b, out=buf[..., :cout])
+    monkeypatch.setenv("FD_SMALLCIN_TC", "0")
+    direct = ops.conv3x3_small_in(x, wp, b)
+    ref = F.conv2d(x.float(), w.float(), b, padding=1).permute(0, 2, 3, 1)
+    assert rel(buf[..., :cout], ref) < 5e-3 and rel(direct, ref) < 5e-3 and float(buf[..., cout:].abs().max()) == 0.0
+
+
 def test_batch_axis_attention(ops):
     torch.manual_seed(8)
     G, L, HW, E, heads = 2, 2, 300, 640, 8
