@@ -382,7 +382,18 @@ __device__ __forceinline__ float max3_f(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
   return r;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+// sigmoid(z) = (1 + tanh(z/2)) / 2: ONE MUFU op (tanh.approx, relative error 2^-11 — a quarter of a bf16 rounding step) and two FMAs
+// instead of exp + an IEEE division (~20 instructions): the activation epilogues of short-K GEMMs (the FaithDiff stem's MLP: K = 640,
+// 128 outputs per thread and tile) were bound by it, not by the MMA.
+__device__ __forceinline__ float tanh_approx_f(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx_f(h), h);
+}
 // Exact-erf GELU (torch's default `gelu`), with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. the same
 // ~4.5e-7 absolute error on gelu as an fp32 evaluation through erff) in 16 instructions / 2 MUFU instead of erff's ~40
 // with selects: the GEGLU epilogue of the feed-forward GEMM evaluates this 16 times per thread and 32-column chunk.
@@ -398,7 +409,10 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   const float r = copysignf(fmaf(-poly, e, 1.f), x);       // erf(x / sqrt 2)
   return 0.5f * x * (1.f + r);
 }
-__device__ __forceinline__ float quick_gelu_f(float x) { return x / (1.f + __expf(-1.702f * x)); }
+__device__ __forceinline__ float quick_gelu_f(float x) {          // x * sigmoid(1.702 x)
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx_f(0.851f * x), h);
+}
 #endif  // __CUDACC__
 
 }  // namespace fd

@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             __syncwarp();
           }
           const float* bs = bias_w + ((c - chalf) >> 1) * 32;
-          if (act == 2) {
+          if (kEpi != 3 && act == 2) {
             float o[16];
             geglu16(o, v, bs);
             uint8_t* rowp = slot + lane * 32;
@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             __syncwarp();                           // lane 0 may re-arm the slot for a residual load below
           }
           if (lane == 0) {
-            const int oc = act == 2 ? (n0 >> 1) : n0;
+            const int oc = (kEpi != 3 && act == 2) ? (n0 >> 1) : n0;
             if (p.mode == 0) tma_store_2d(&p.omap, slot, oc, box_row0);
             else tma_store_4d(&p.omap, slot, oc, bx, by, bimg);
             bulk_commit();
@@ -897,11 +897,14 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
   p.act = d->act; p.bias_along_m = d->bias_along_m; p.out_fp32 = d->out_fp32;
 
   // epilogue specialisation: 1 = TMA epilogue, no activation (bias / per-sample bias / residual optional);
-  // 2 = TMA epilogue, GEGLU with column bias; 0 = generic (every option at run time, direct stores possible)
+  // 2 = TMA epilogue, GEGLU with column bias; 3 = TMA epilogue with an elementwise activation chosen at run time (SiLU / quick-GELU /
+  // GELU / LeakyReLU: the FaithDiff stem's MLP, the condition embedding, the text encoders, BSRNet — they ran through the generic
+  // kernel at a third of the specialised ones' rate); 0 = generic (every option at run time, direct stores possible)
   int epi = 0;
   if (p.tma_epi && !d->bias_along_m) {
     if (d->act == 0) epi = 1;
     else if (d->act == 2 && !d->rowbias && !d->residual) epi = 2;
+    else if (d->act != 2) epi = 3;
   }
   {
     static int env_generic = -1;
@@ -931,16 +934,17 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
   static const KernelFn kernels_gn[2] = {gemm_tcgen05_kernel<false, 1, 3>, gemm_tcgen05_kernel<true, 1, 3>};
   static const KernelFn kernels_ln[6] = {gemm_tcgen05_kernel<false, 1, 1>, gemm_tcgen05_kernel<false, 2, 1>, gemm_tcgen05_kernel<false, 1, 2>,
                                          gemm_tcgen05_kernel<true, 1, 1>,  gemm_tcgen05_kernel<true, 2, 1>,  gemm_tcgen05_kernel<true, 1, 2>};
-  static const KernelFn kernels[6] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
-                                      gemm_tcgen05_kernel<true, 0>,  gemm_tcgen05_kernel<true, 1>,  gemm_tcgen05_kernel<true, 2>};
+  static const KernelFn kernels[8] = {gemm_tcgen05_kernel<false, 0>, gemm_tcgen05_kernel<false, 1>, gemm_tcgen05_kernel<false, 2>,
+                                      gemm_tcgen05_kernel<false, 3>, gemm_tcgen05_kernel<true, 0>,  gemm_tcgen05_kernel<true, 1>,
+                                      gemm_tcgen05_kernel<true, 2>,  gemm_tcgen05_kernel<true, 3>};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int i = 0; i < 6; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int i = 0; i < 8; ++i) FD_CHECK_CUDA(cudaFuncSetAttribute(kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int csize = p.cm * p.cn;
   const int num_super = p.m_super * p.n_super;
-  KernelFn kernel = kernels[(p.pair ? 3 : 0) + epi];
+  KernelFn kernel = kernels[(p.pair ? 4 : 0) + epi];
   if (ln_in || ln_out) {
     static bool ln_attr_set = false;
     if (!ln_attr_set) {
