@@ -1,5 +1,6 @@
 // Flash-style attention for head_dim 64 on tcgen05 (sm_100a), bf16 in/out, fp32 softmax + accumulation.
-// One CTA = one (batch, head, 128-query block); two CTAs co-reside per SM so one CTA's softmax overlaps the other's MMAs.
+// One CTA = one (batch, head, 128-query block); three CTAs (64-key blocks; two with 128-key blocks) co-reside per SM so one CTA's
+// softmax overlaps the others' MMAs and latency-bound phases.
 //   warp 0 lane 0 : TMA producer  (Q once; K and V 128-key blocks in separate 2-stage rings, 128B swizzle.  K_j is released
 //                                 as soon as S_j = Q K_j^T has been computed, so K_{j+2} streams in two blocks ahead)
 //   warp 1 lane 0 : MMA issuer    S_{j+1} = Q K_{j+1}^T (M128 N128 K64) -> TMEM cols [0,128) is issued as soon as the softmax
