@@ -53,9 +53,8 @@ struct GemmKParams {
   float ln_inv_c, ln_eps;
   float2* ln_stats_out;
   int ln_out_ld;
-  // GroupNorm statistics from the producer (kLn = 3): per (column pair, 32-row epilogue box) sum / sum of squares of the
-  // bf16-rounded outputs, float2 [N / 2, gn_ld] (pair-major: the consumer's per-group reduction reads whole rows); the consumer
-  // GroupNorm becomes a single streaming pass (norm.cu)
+  // GroupNorm statistics from the producer (kLn = 3): per (32-row epilogue box, column pair) sum / sum of squares of the
+  // bf16-rounded outputs, float2 [4 * m_tiles, gn_ld]; the consumer GroupNorm becomes a single streaming pass (norm.cu)
   float2* gn_stats_out;
   int gn_ld;
 };
@@ -531,7 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tcgen05_kernel(const __grid_
             ssum += __shfl_xor_sync(0xffffffffu, ssum, 16);
             qsum += __shfl_xor_sync(0xffffffffu, qsum, 16);
             if (hf == 0 && n0 + 2 * pr < p.N)
-              p.gn_stats_out[(long long)((n0 >> 1) + pr) * p.gn_ld + (m_blk * 4 + quad)] = make_float2(ssum, qsum);
+              p.gn_stats_out[(long long)(m_blk * 4 + quad) * p.gn_ld + (n0 >> 1) + pr] = make_float2(ssum, qsum);
             __syncwarp();                           // lane 0 may re-arm the slot for a residual load below
           }
           if (lane == 0) {
@@ -926,7 +925,7 @@ static int gemm_impl(const fd_gemm_desc* d, fd_gemm_ln_desc* ln, void* stream_) 
     ln->stats_out_n = 2 * p.n_tiles;
   }
   if (gn_out) {
-    FD_REQUIRE(epi == 1 && d->N % 2 == 0 && ln->colstats_ld >= 4 * p.m_tiles, "fd_gemm_ln: column statistics need the linear TMA epilogue and colstats_ld >= 4 * tiles");
+    FD_REQUIRE(epi == 1 && d->N % 2 == 0 && ln->colstats_ld >= d->N / 2, "fd_gemm_ln: column statistics need the linear TMA epilogue");
     p.gn_stats_out = (float2*)ln->colstats_out; p.gn_ld = (int)ln->colstats_ld;
     ln->colstats_boxes = 4 * p.m_tiles;
     ln->colstats_boxes_per_image = d->mode == 0 ? 0 : 4 * p.tiles_per_img;

@@ -381,7 +381,7 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x0, int c0, const __nv_bfloat1
 // combine of the group's box partials of up to two concatenated sources, in box order (deterministic), -> per-(sample, channel)
 // scale / shift; (2) gn_apply_stream_kernel: y = silu(x*scale + shift), 8 16-byte loads in flight per thread.
 struct GnStatSrc {
-  const float2* stats;   // [channel pairs, ld] (sum, sum of squares) per (channel pair, box); box columns: segment-major, then sample
+  const float2* stats;   // [segments * seg_stride_boxes, ld] (sum, sum of squares) per (box, channel pair)
   long long ld;
   int boxes_per_sample, segments;
   long long seg_stride_boxes;
@@ -401,20 +401,19 @@ __global__ void __launch_bounds__(256) gn_stats_finalize_kernel(GnStatSrc s0, in
     const int base_pair = src ? c0 / 2 : 0, npairs_src = (src ? c1 : c0) / 2;
     const int lo = max(pair_lo - base_pair, 0), hi = min(pair_hi - base_pair, npairs_src);
     if (!S.stats || lo >= hi) continue;
-    // (pair, segment, box) flattened, boxes fastest: the boxes of sample b in one (pair, segment) are contiguous -> coalesced loads,
-    // and small images (32 boxes per sample) still keep all 256 threads busy across the group's pairs
-    const int bps = S.boxes_per_sample, per_pair = bps * S.segments;
-    const int total = (hi - lo) * per_pair;
-    float fs = 0.f, fq = 0.f;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-      const int pp = i / per_pair, rem = i - pp * per_pair;
-      const int seg = rem / bps, r = rem - seg * bps;
-      const float2 t = __ldg(S.stats + (long long)(lo + pp) * S.ld + seg * S.seg_stride_boxes + (long long)b * bps + r);
-      fs += t.x;
-      fq += t.y;
+    const long long nbox = (long long)S.boxes_per_sample * S.segments;
+    for (long long i = threadIdx.x; i < nbox; i += blockDim.x) {
+      const long long seg = i / S.boxes_per_sample, r = i - seg * S.boxes_per_sample;
+      const float2* row = S.stats + (seg * S.seg_stride_boxes + (long long)b * S.boxes_per_sample + r) * S.ld;
+      float fs = 0.f, fq = 0.f;
+      for (int pp = lo; pp < hi; ++pp) {
+        const float2 t = __ldg(row + pp);
+        fs += t.x;
+        fq += t.y;
+      }
+      s += (double)fs;
+      q += (double)fq;
     }
-    s += (double)fs;
-    q += (double)fq;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -33,21 +33,19 @@ class RowStats:
 
 
 class ColStats:
-    """Per-(channel pair, 32-row box) (sum, sum of squares) a producer conv / GEMM leaves for the GroupNorm that consumes its
-    output (fd_gemm_ln colstats_out -> fd_groupnorm_nhwc_from_stats): fp32 [pairs, ld, 2], box columns segment-major then sample.
-    Travels as the `_fd_colstats` attribute of the output tensor object; any op that makes a new tensor drops it and the consumer
-    falls back to the two-pass GroupNorm."""
+    """Per-(32-row box, channel pair) (sum, sum of squares) a producer conv / GEMM leaves for the GroupNorm that consumes its
+    output (fd_gemm_ln colstats_out -> fd_groupnorm_nhwc_from_stats).  Travels as the `_fd_colstats` attribute of the output
+    tensor object; any op that makes a new tensor drops it and the consumer falls back to the two-pass GroupNorm."""
     __slots__ = ("buf", "ld", "boxes_per_sample", "segments", "seg_stride")
 
-    def __init__(self, buf, boxes_per_sample, segments=1, seg_stride=0):
-        self.buf, self.ld, self.boxes_per_sample, self.segments, self.seg_stride = buf, buf.shape[1], boxes_per_sample, segments, seg_stride
+    def __init__(self, buf, ld, boxes_per_sample, segments=1, seg_stride=0):
+        self.buf, self.ld, self.boxes_per_sample, self.segments, self.seg_stride = buf, ld, boxes_per_sample, segments, seg_stride
 
     def select_samples(self, index, n_src):
         """Statistics of x.index_select(0, index) for x of n_src samples (single segment)."""
         assert self.segments == 1
-        bps = self.boxes_per_sample
-        b = self.buf[:, :n_src * bps].reshape(self.buf.shape[0], n_src, bps, 2).index_select(1, index)
-        return ColStats(b.reshape(self.buf.shape[0], -1, 2).contiguous(), bps)
+        b = self.buf[:n_src * self.boxes_per_sample].view(n_src, self.boxes_per_sample, self.ld, 2).index_select(0, index)
+        return ColStats(b.reshape(-1, self.ld, 2).contiguous(), self.ld, self.boxes_per_sample)
 
 
 GN_STATS = __import__("os").environ.get("FD_GN_STATS", "1") == "1"
@@ -105,11 +103,11 @@ def gemm(a, w, a2=None, bias=None, rowbias=None, rows_per_batch=0, residual=None
             and out.dtype == BF16 and not bias_along_m and ln_in is None and not stats_out and N % 16 == 0):
         # GroupNorm statistics for the consumer of `out`: per (32-row box, column pair), tiles never straddle a sample
         lnd = GemmLnDesc()
-        buf = torch.empty((N // 2, (M + 127) // 128 * 4, 2), device=a.device, dtype=torch.float32)
-        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), buf.shape[1]
+        buf = torch.empty(((M + 127) // 128 * 4, N // 2, 2), device=a.device, dtype=torch.float32)
+        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), N // 2
         check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(colstats)")
-        assert lnd.colstats_boxes == buf.shape[1]
-        return tag_stats(out, ColStats(buf, colstats_rows_per_sample // 32))
+        assert lnd.colstats_boxes == buf.shape[0]
+        return tag_stats(out, ColStats(buf, N // 2, colstats_rows_per_sample // 32))
     if ln_in is None and not stats_out:
         check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm")
         return out
@@ -173,11 +171,11 @@ def conv3x3(x, w, x2=None, bias=None, rowbias=None, residual=None, act=0, stride
     if colstats and GN_STATS and act == 0 and N % 16 == 0:
         lnd = GemmLnDesc()
         bps = 4 * _conv_tiles(Ho, Wo)
-        buf = torch.empty((N // 2, B * bps, 2), device=x.device, dtype=torch.float32)
-        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), buf.shape[1]
+        buf = torch.empty((B * bps, N // 2, 2), device=x.device, dtype=torch.float32)
+        lnd.colstats_out, lnd.colstats_ld = buf.data_ptr(), N // 2
         check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(conv, colstats)")
-        assert lnd.colstats_boxes == buf.shape[1] and lnd.colstats_boxes_per_image == bps, (lnd.colstats_boxes, buf.shape, bps)
-        return tag_stats(out, ColStats(buf, bps))
+        assert lnd.colstats_boxes == buf.shape[0] and lnd.colstats_boxes_per_image == bps, (lnd.colstats_boxes, buf.shape, bps)
+        return tag_stats(out, ColStats(buf, N // 2, bps))
     check(lib.fd_gemm(C.byref(d), _stream()), "fd_gemm(conv)")
     return out
 
@@ -196,7 +194,7 @@ def conv3x3_upsampled2x(x, w_phases, bias=None, out=None, colstats=False):
     st = None
     if colstats and GN_STATS and N % 16 == 0:
         bps = 4 * _conv_tiles(H, W)                    # per phase: the phase's output grid is the input grid
-        st = ColStats(torch.empty((N // 2, 4 * B * bps, 2), device=x.device, dtype=torch.float32), bps, 4, B * bps)
+        st = ColStats(torch.empty((4 * B * bps, N // 2, 2), device=x.device, dtype=torch.float32), N // 2, bps, 4, B * bps)
     for ph in range(4):
         w = w_phases[ph]
         assert w.is_contiguous() and w.shape == (N, 4 * C0)
@@ -208,7 +206,7 @@ def conv3x3_upsampled2x(x, w_phases, bias=None, out=None, colstats=False):
         d.out, d.ld_out, d.alpha = out.data_ptr(), out.stride(2), 1.0
         if st is not None:
             lnd = GemmLnDesc()
-            lnd.colstats_out, lnd.colstats_ld = st.buf[:, ph * st.seg_stride:].data_ptr(), st.ld
+            lnd.colstats_out, lnd.colstats_ld = st.buf[ph * st.seg_stride:].data_ptr(), N // 2
             check(lib.fd_gemm_ln(C.byref(d), C.byref(lnd), _stream()), "fd_gemm_ln(upsampled conv, colstats)")
             assert lnd.colstats_boxes == st.seg_stride
         else:

@@ -83,11 +83,11 @@ typedef struct fd_gemm_ln_desc {
   int64_t stats_out_ld;  /* >= 2 * ceil(N / block_n); 2 * ceil(N / 32) always suffices                   */
   int32_t stats_out_n;   /* OUT: slots written per row                                                   */
   int32_t pad1_;
-  /* GroupNorm statistics from the producer: per (column pair, 32-row epilogue box) sum / sum of squares of the bf16-rounded
-   * outputs, so that fd_groupnorm_nhwc_from_stats normalises in ONE streaming pass.  Box 4 t + r = rows [128 t + 32 r, +32)
+  /* GroupNorm statistics from the producer: per (32-row epilogue box, column pair) sum / sum of squares of the bf16-rounded
+   * outputs, so that fd_groupnorm_nhwc_from_stats normalises in ONE streaming pass.  Box r of tile t = rows [128 t + 32 r, +32)
    * (mode 0) / the r-th 32-pixel quarter of the t-th pixel patch (conv modes; a patch never crosses an image).              */
-  void* colstats_out;    /* float2 [N / 2, colstats_ld] (pair-major), or NULL                            */
-  int64_t colstats_ld;   /* box columns per pair row, >= colstats_boxes                                  */
+  void* colstats_out;    /* float2 [>= colstats_boxes, colstats_ld], or NULL                             */
+  int64_t colstats_ld;   /* >= N / 2                                                                     */
   int32_t colstats_boxes;            /* OUT: box rows written = 4 * number of 128-row tiles              */
   int32_t colstats_boxes_per_image;  /* OUT: conv modes: 4 * tiles per image; mode 0: 0                  */
 } fd_gemm_ln_desc;
@@ -146,7 +146,7 @@ int fd_groupnorm_nhwc_fused(const void* x0, int32_t c0, const void* x1, int32_t 
                             void* out, int32_t batch, int64_t hw, int32_t groups, float eps, int32_t silu, float* work,
                             void* sync, void* stream);
 /* GroupNorm(+SiLU) in ONE streaming pass over x, from statistics its producer left behind (fd_gemm_ln with colstats_out):
- * stats_k = float2 [c_k / 2, ld_k] per (channel pair, 32-row box) of source k; sample b owns box columns
+ * stats_k = float2 [segments_k * seg_stride_k, ld_k] per (32-row box, channel pair) of source k; sample b owns box rows
  * [s * seg_stride_k + b * boxes_per_sample_k, + boxes_per_sample_k) of every segment s (segments > 1: the four output phases of a
  * mode-3 upsampling conv).  A tiny finalize launch (one CTA per sample and group, fp64 combine in box order) writes the per-channel
  * scale / shift into work (>= 2 * batch * (c0 + c1) floats); the apply launch reads x once and writes y once.  Same call sites as

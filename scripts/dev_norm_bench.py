@@ -70,7 +70,7 @@ if "gns" in sys.argv or len(sys.argv) == 1:
         xs = [torch.randn(B, H, H, C, device="cuda").to(BF) for _ in range(nb)]
         for x in xs:     # fabricate the producer's statistics: per (32-row box, channel pair) sum / sum of squares, mode-0 box layout
             v = x.view(B * H * H // 32, 32, C // 2, 2).float()
-            ops.tag_stats(x, ops.ColStats(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).transpose(0, 1).contiguous(), H * H // 32))
+            ops.tag_stats(x, ops.ColStats(torch.stack([v.sum((1, 3)), (v * v).sum((1, 3))], -1).contiguous(), C // 2, H * H // 32))
         gm, bt = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
         out = torch.empty_like(xs[0])
         i = [0]
