@@ -300,3 +300,52 @@ def test_fold_layernorm_host_preparation():
         out = rstd * (xf @ wp.float().t()) - rstd * mean * cs + bp
         ref = torch.nn.functional.layer_norm(xf, (Cc,), gamma, beta, 1e-5) @ ww.float().t() + (bias if bias is not None else 0)
         assert ((out - ref).norm() / ref.norm()).item() < 3e-3
+
+
+def test_upsample_phase_weights_reproduce_conv_over_nearest_upsample():
+    """blocks.upsample_phase_weights (host half of fd_gemm mode 3): the four 2x2-tap phase convs with pre-summed weights equal
+    conv3x3(nearest_upsample_2x(x)) including the zero padding of the UPSAMPLED image (Upsample2D, …extension.py:661-684)."""
+    import torch
+    import torch.nn.functional as F
+    from faithdiff_dev_b200.blocks import upsample_phase_weights
+    torch.manual_seed(0)
+    w, x = torch.randn(6, 5, 3, 3), torch.randn(2, 5, 7, 9)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w.to(torch.bfloat16).float(), padding=1)
+    wp = upsample_phase_weights(w)
+    assert len(wp) == 4 and all(p.shape == (6, 20) and p.dtype == torch.bfloat16 for p in wp)
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for b in range(2):
+            k = wp[a * 2 + b].float().reshape(6, 2, 2, 5).permute(0, 3, 1, 2)          # [O, I, 2, 2], taps (i-1+a+r', j-1+b+s')
+            out[:, :, a::2, b::2] = F.conv2d(xp[:, :, a:a + 8, b:b + 10], k)
+    assert ((out - ref).norm() / ref.norm()).item() < 5e-3                                 # bf16 rounding of the summed taps only
+
+
+def test_tiled_stage_assignment_is_balanced_and_deterministic():
+    """vae.assign_tiles: owner rank of each tile of a tiled one-time stage by area (edge tiles are smaller).  4K LQ encoder: 3 x 5
+    tiles of 1024 px at stride 768 over 2160 x 3840 — twelve full tiles and three 624-row ones."""
+    from faithdiff_dev_b200.vae import assign_tiles
+    areas = []
+    for i in range(0, 2160, 768):
+        for j in range(0, 3840, 768):
+            areas.append(min(1024, 2160 - i) * min(1024, 3840 - j))
+    assert len(areas) == 15
+    for world in (2, 4, 8):
+        owner = assign_tiles(areas, world)
+        assert owner == assign_tiles(list(areas), world) and set(owner) == set(range(world))
+        load = [sum(a for a, o in zip(areas, owner) if o == r) for r in range(world)]
+        ideal = sum(areas) / world
+        assert max(load) <= ideal + max(areas)                  # greedy largest-first: within one tile of the mean
+        rr = [sum(a for n, a in enumerate(areas) if n % world == r) for r in range(world)]
+        assert max(load) <= max(rr)                             # never worse than round-robin
+
+
+def test_conv_patch_rule_mirrors_the_kernel():
+    """ops._conv_tiles mirrors gemm_tcgen05.cu pick_patch (the 128-pixel patch w x 128/w that wastes least, widest first): it sizes
+    the GroupNorm-statistics buffers, and the C side re-checks the count (colstats_boxes) on every call."""
+    from faithdiff_dev_b200.ops import _conv_tiles
+    assert _conv_tiles(128, 128) == 128 and _conv_tiles(64, 64) == 32 and _conv_tiles(32, 32) == 8
+    assert _conv_tiles(8, 8) == 1                               # 16 x 8 patch covers it
+    assert _conv_tiles(24, 40) == 9                             # 16 x 8 patches: 3 columns x 3 rows waste 1.2x (8 x 16: 1.33x, 64 x 2: 1.6x)
+    assert _conv_tiles(18, 14) == 3 and _conv_tiles(135, 240) == 255
