@@ -394,8 +394,11 @@ class FaithDiffStableDiffusionXLPipeline:
             cond_all[n0_:n0_ + len(part)].copy_(unet.condition_embed(lq_tiles))
         ids_all = torch.tensor([[original_size[0], original_size[1], i, j, target_size[0], target_size[1]] for i, j in idx],
                                dtype=torch.float32).to(dt).to(torch.float32)   # rounded through the working dtype
-        temb_table = unet.time_embedding_table(ts, te, ids_all.to(dev))          # [S, T, 2, ΣC]: all (step, tile) biases
-        temb_units = temb_table.reshape(temb_table.shape[0], 2 * T, -1)          # [S, U, ΣC], u = 2*tile + branch
+        # [S, T_mine, 2, ΣC]: the per-resnet time biases of every (step, tile of THIS rank) — 140 small-M launches over the 52 MB
+        # stacked time_emb_proj at 4K, so a rank computes only its own tiles' rows (at N = 8 it was 21 of the stage's 54 ms)
+        temb_table = unet.time_embedding_table(ts, te, ids_all[my_tiles[0]:my_tiles[-1] + 1].to(dev))
+        temb_units = temb_table.reshape(temb_table.shape[0], 2 * len(my_tiles), -1)   # [S, U_mine, ΣC], local u = 2*(tile - first) + branch
+        u_first = 2 * my_tiles[0]
         if self.world_size == 1:
             groups = [[u for t in g for u in (2 * t, 2 * t + 1)]
                       for g in plan_launch_groups(list(range(T)), range(1, max(1, self.tiles_per_launch) + 1))]
@@ -414,7 +417,8 @@ class FaithDiffStableDiffusionXLPipeline:
                 self._graphs[key] = TileStepGraph(unet, kv, lk, slot, branch, k1, k2, dt, add_sample, self.use_cuda_graph)
             assert gt == list(range(gt[0], gt[-1] + 1)), "launch groups are contiguous tile ranges"
             c_lo = my_tiles.index(gt[0])
-            plans.append((self._graphs[key], (gt[0], gt[-1] + 1), (c_lo, c_lo + len(gt)), torch.tensor(g, device=dev, dtype=torch.long)))
+            plans.append((self._graphs[key], (gt[0], gt[-1] + 1), (c_lo, c_lo + len(gt)),
+                          torch.tensor([u - u_first for u in g], device=dev, dtype=torch.long)))
         for key, gobj in self._graphs.items():
             if key != "key" and (kv_fresh or getattr(gobj, "_kv_id", None) is not kv):
                 gobj.set_text_kv(kv)
