@@ -12,3 +12,4 @@ from .color_fix import adain_color_fix, wavelet_color_fix  # noqa: F401
 from .create_model import FaithDiff_pipeline, quantize_8bit_state_dict  # noqa: F401
 from .image_process import check_image_size, resize_lanczos  # noqa: F401
 from .bsrnet import RRDBNet, create_bsrnet  # noqa: F401
+from .png import encode_png, save_png  # noqa: F401

@@ -47,6 +47,9 @@ lib.fd_groupnorm_work_floats.restype = C.c_int64
 lib.fd_groupnorm_sync_bytes.restype = C.c_int64
 lib.fd_peer_region_bytes.restype = C.c_int64
 lib.fd_colorfix_work_floats.restype = C.c_int64
+lib.fd_png_filtered_bytes.restype = C.c_int64
+lib.fd_png_work_words.restype = C.c_int64
+lib.fd_png_file_capacity.restype = C.c_int64
 
 i32, i64, f32, vp = C.c_int32, C.c_int64, C.c_float, C.c_void_p
 _SIGS = {
@@ -97,6 +100,10 @@ _SIGS = {
     "fd_colorfix_work_floats": [i32, i32],
     "fd_adain_color_fix": [vp, vp, vp, i32, i32, vp, vp],
     "fd_wavelet_color_fix": [vp, vp, vp, i32, i32, vp, vp],
+    "fd_png_filtered_bytes": [i32, i32, i32],
+    "fd_png_work_words": [i32, i32, i32],
+    "fd_png_file_capacity": [i32, i32, i32],
+    "fd_png_encode": [vp, i32, i32, i32, i64, vp, vp, vp, i64, vp, vp],
 }
 EXPORTS = ["fd_last_error", "fd_version", "fd_launch_count", "fd_sizeof_gemm_desc", "fd_sizeof_gemm_ln_desc"] + list(_SIGS)
 for _n, _a in _SIGS.items():

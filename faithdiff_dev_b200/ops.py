@@ -583,5 +583,23 @@ def color_fix(target_u8, source_u8, mode):
     return out
 
 
+def png_encode(img):
+    """Complete PNG file of a u8 [H, W, C] device image (C = 1..4; rows may be strided, e.g. a crop of a larger image).
+    Returns (file buffer u8 on the device, result int64 [2] on the device: bytes used, overflow flag) without synchronising."""
+    assert img.dtype == torch.uint8 and img.dim() == 3 and img.is_cuda
+    H, W, Cc = img.shape
+    if img.stride(2) != 1 or img.stride(1) != Cc or img.stride(0) < W * Cc:
+        img = img.contiguous()
+    dev = img.device
+    filtered = torch.empty(lib.fd_png_filtered_bytes(H, W, Cc), device=dev, dtype=torch.uint8)
+    work = torch.empty((lib.fd_png_work_words(H, W, Cc) + 1) // 2, device=dev, dtype=torch.int64)
+    cap = lib.fd_png_file_capacity(H, W, Cc)
+    out = torch.empty(cap // 4, device=dev, dtype=torch.int32).view(torch.uint8)
+    result = torch.empty(2, device=dev, dtype=torch.int64)
+    check(lib.fd_png_encode(_p(img), H, W, Cc, img.stride(0), _p(filtered), _p(work), _p(out), cap, _p(result), _stream()),
+          "fd_png_encode")
+    return out, result
+
+
 def launch_count():
     return int(lib.fd_launch_count())

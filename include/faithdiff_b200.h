@@ -296,6 +296,19 @@ int fd_adain_color_fix(const uint8_t* target, const uint8_t* source, uint8_t* ou
                        void* stream);
 int fd_wavelet_color_fix(const uint8_t* target, const uint8_t* source, uint8_t* out, int32_t h, int32_t w, float* work,
                          void* stream);
+/* PNG encoder: the caller's `out_image.save(path)` (test_wo_llava.py:97, test.py:130; PIL's PngImagePlugin + host zlib there) on
+ * the device.  image: u8 [h, w, channels] with `row_stride_bytes` between rows (a cropped view is fine), channels 1 / 2 / 3 / 4 =
+ * grey / grey+alpha / RGB / RGBA, 8 bits.  Writes a COMPLETE PNG file (signature, IHDR, IDAT chunks with their CRCs, IEND) into
+ * `out`; result[0] = file bytes, result[1] = 1 if `out_capacity` was too small (nothing usable written) — device memory, read
+ * it after synchronising the stream.  Adaptive per-row filtering (minimum sum of absolute values), one dynamic-Huffman deflate
+ * block per 16 KB of filtered data with run matches at distance 1, byte-aligned between blocks; lossless, decodes with any PNG
+ * reader (the test oracle is PIL + zlib).  filtered: scratch of fd_png_filtered_bytes; work: fd_png_work_words 32-bit words,
+ * 8-byte aligned; out: 4-byte aligned, fd_png_file_capacity bytes always suffice.  Five launches, no host synchronisation. */
+int64_t fd_png_filtered_bytes(int32_t h, int32_t w, int32_t channels);
+int64_t fd_png_work_words(int32_t h, int32_t w, int32_t channels);
+int64_t fd_png_file_capacity(int32_t h, int32_t w, int32_t channels);
+int fd_png_encode(const uint8_t* image, int32_t h, int32_t w, int32_t channels, int64_t row_stride_bytes, uint8_t* filtered,
+                  uint32_t* work, uint8_t* out, int64_t out_capacity, int64_t* result, void* stream);
 
 #ifdef __cplusplus
 }

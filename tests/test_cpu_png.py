@@ -1,0 +1,144 @@
+"""Device PNG encoder (csrc/png_core.cuh + png.cu), CPU side: the per-thread phase functions run on the host
+(tests/png_host_emul.cpp) and are checked against the reference's own encoder stack — PIL (PngImagePlugin) and zlib
+(`out_image.save(path)`, test_wo_llava.py:97) — plus numpy restatements of the PNG filter rule and of Huffman optimality."""
+import heapq
+import io
+import struct
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+import png_emul
+
+
+def _chunks(data):
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, out = 8, []
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        (crc,) = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+        assert crc == zlib.crc32(typ + body) & 0xffffffff, typ
+        out.append((typ, body))
+        pos += 12 + n
+    assert pos == len(data)
+    return out
+
+
+def _filter_oracle(a):
+    """numpy restatement of PNG filtering with the minimum-sum-of-absolute-values choice (lowest index on ties)."""
+    h, w, c = a.shape
+    rb = w * c
+    rows = a.reshape(h, rb).astype(np.int32)
+    out = bytearray()
+    prev = np.zeros(rb, np.int32)
+    for y in range(h):
+        cur = rows[y]
+        left = np.concatenate([np.zeros(c, np.int32), cur[:-c]]) if rb > c else np.zeros(rb, np.int32)
+        ul = np.concatenate([np.zeros(c, np.int32), prev[:-c]]) if rb > c else np.zeros(rb, np.int32)
+        p = left + prev - ul
+        pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - ul)
+        pae = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+        cands = [cur, cur - left, cur - prev, cur - ((left + prev) >> 1), cur - pae]
+        cands = [(v & 255).astype(np.uint8) for v in cands]
+        cost = [int(np.where(v < 128, v.astype(np.int64), 256 - v.astype(np.int64)).sum()) for v in cands]
+        f = int(np.argmin(cost))
+        out.append(f)
+        out += cands[f].tobytes()
+        prev = cur
+    return bytes(out)
+
+
+IMAGES = png_emul.test_images()
+
+
+@pytest.mark.parametrize("name", sorted(IMAGES))
+def test_emulated_encoder_decodes_with_pil_and_zlib(name):
+    a = IMAGES[name]
+    data, filt = png_emul.encode(a)
+    a3 = a if a.ndim == 3 else a[..., None]
+    h, w, c = a3.shape
+    # container: signature, IHDR, IDAT..., IEND, every CRC right (checked in _chunks)
+    ch = _chunks(data)
+    assert ch[0][0] == b"IHDR" and ch[-1] == (b"IEND", b"") and all(t == b"IDAT" for t, _ in ch[1:-1])
+    assert struct.unpack(">IIBBBBB", ch[0][1]) == (w, h, 8, {1: 0, 2: 4, 3: 2, 4: 6}[c], 0, 0, 0)
+    assert len(ch) - 2 == -(-len(filt) // 16384)
+    # the zlib stream (Adler-32 included) inflates to the filtered scanlines, which follow the PNG filter rule
+    assert zlib.decompress(b"".join(b for _, b in ch[1:-1])) == filt
+    assert filt == _filter_oracle(np.ascontiguousarray(a3))
+    # and PIL, the reference's own codec, reads back the exact pixels
+    im = Image.open(io.BytesIO(data))
+    im.load()
+    back = np.asarray(im)
+    assert back.shape == np.squeeze(a3, -1).shape if c == 1 else back.shape == a3.shape
+    assert (back.reshape(a3.shape) == a3).all()
+
+
+def test_compression_is_in_pil_range():
+    """Not a parity quantity (two encoders never produce the same file) — a sanity band against PIL's default encoder."""
+    for name, lo, hi in (("smooth_rgb", 0.0, 1.05), ("rgba", 0.0, 1.05), ("noise", 0.0, 1.05), ("mixed", 0.0, 1.15)):
+        a = IMAGES[name]
+        buf = io.BytesIO()
+        Image.fromarray(np.squeeze(a)).save(buf, format="PNG")
+        ours = len(png_emul.encode(a)[0])
+        assert lo <= ours / len(buf.getvalue()) <= hi, (name, ours, len(buf.getvalue()))
+    flat = IMAGES["zeros"]
+    assert len(png_emul.encode(flat)[0]) < flat.size // 40            # runs: far below the 1 bit per byte of literals only
+
+
+def test_capacity_overflow_is_reported():
+    with pytest.raises(OverflowError):
+        png_emul.encode(IMAGES["noise"], capacity=4096)
+
+
+def _optimal_cost(freq):
+    h = [(f, i) for i, f in enumerate(freq) if f]
+    heapq.heapify(h)
+    cost, n = 0, len(freq)
+    while len(h) > 1:
+        a, b = heapq.heappop(h), heapq.heappop(h)
+        cost += a[0] + b[0]
+        heapq.heappush(h, (a[0] + b[0], n))
+        n += 1
+    return cost
+
+
+def test_huffman_lengths_complete_limited_and_optimal():
+    rng = np.random.default_rng(1)
+    fib = [1, 1]
+    while len(fib) < 40:
+        fib.append(fib[-1] + fib[-2])
+    cases = [(rng.integers(0, 1000, 286), 15), (rng.integers(1, 5, 286), 15), (np.array(fib[:30]), 15), (np.array(fib[:19]), 7),
+             (np.array([5, 0, 0, 9] + [0] * 15), 7), (np.array([0, 0, 7] + [0] * 16), 7), (np.array([1] * 19), 7),
+             (np.concatenate([rng.integers(0, 3, 200), [16000], rng.integers(0, 3, 85)]), 15)]
+    for freq, maxbits in cases:
+        freq = np.asarray(freq, np.uint32)
+        lens = png_emul.huffman_lengths(freq, maxbits).astype(np.int64)
+        used = freq > 0
+        assert lens.max() <= maxbits
+        if used.sum() >= 2:
+            assert ((lens > 0) == used).all()
+            assert sum(2.0 ** -int(l) for l in lens[used]) == 1.0          # complete prefix code (zlib rejects anything else)
+            cost, opt = int((lens * freq).sum()), _optimal_cost(freq.tolist())
+            assert cost >= opt
+            if max(len(bin(int(f))) for f in freq) < 12 and maxbits == 15 and used.sum() > 20 and freq.max() < 1200:
+                assert cost == opt                                          # limit not reached: the tree is the optimal one
+            # where the length limit bites (Fibonacci statistics) the repaired code is no longer optimal: a loose band
+            assert cost <= opt * (1.15 if lens.max() == maxbits else 1.0) + 8
+        else:
+            assert lens[used].tolist() == [1] and (lens > 0).sum() == 2   # lone symbol paired with a dummy: still complete
+
+
+def test_no_cpu_path():
+    import torch
+    import faithdiff_dev_b200 as fd
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        fd.encode_png(np.zeros((8, 8, 3), np.uint8), device="cpu")
+    with pytest.raises(ValueError):
+        fd.encode_png(np.zeros((8, 8, 5), np.uint8))
+    with pytest.raises(ValueError):
+        fd.encode_png(np.zeros((8, 8, 3), np.float32))
