@@ -2,10 +2,10 @@
 // raw 24.9 MB 4K image over PCIe and through the host's zlib (1-2 s per 4K image with PIL: more than a whole restoration
 // on 8 GPUs).  Five launches on one stream; the per-thread logic and the file format are in png_core.cuh.
 //   filter  : one CTA per scanline   — adaptive filter choice, filtered row, per-row Adler-32 partials
-//   stats   : one CTA per 16 KB block — byte histogram in shared memory, then the block's Huffman code + header
+//   stats   : one CTA per 16 KB block — block staged in shared memory, token histogram, the block's Huffman code + header
 //   layout  : one CTA                — prefix sum of the block sizes, Adler-32 combine, PNG framing, zlib header / trailer
-//   encode  : one CTA per block      — every thread packs 64 bytes; bit offsets from a per-block scan of code lengths
-//   crc     : one thread per IDAT    — CRC-32 of each chunk (table in shared memory)
+//   encode  : one CTA per block      — every thread packs 64 bytes; bit offsets from a two-level scan of the bit counts
+//   crc     : one CTA per IDAT chunk — per-thread piece CRCs combined through GF(2) multiplications by powers of x
 #include "common.cuh"
 #include "png_core.cuh"
 #include "../../include/faithdiff_b200.h"
@@ -34,11 +34,15 @@ __global__ void __launch_bounds__(kThreads) png_stats_kernel(const uint8_t* __re
   __shared__ StatsShared sh;
   const long long block = blockIdx.x;
   const int tid = threadIdx.x;
-  stats_phase_zero(tid, sh);
+  stats_phase_stage(filt, n_total, block, tid, sh);
   __syncthreads();
-  stats_phase_hist(filt, n_total, block, tid, sh);
+  stats_phase_hist(n_total, block, tid, sh);
   __syncthreads();
-  stats_phase_build(block, codes, hdrs, meta, tid, sh);
+  stats_phase_lengths(tid, sh);
+  __syncthreads();
+  stats_phase_codes(block, codes, tid, sh);
+  __syncthreads();
+  stats_phase_header(block, hdrs, meta, tid, sh);
 }
 
 __global__ void __launch_bounds__(kThreads) png_layout_kernel(int h, int w, int channels, long long nblocks, const BlockMeta* __restrict__ meta,
@@ -61,20 +65,26 @@ __global__ void __launch_bounds__(kThreads) png_encode_kernel(const uint8_t* __r
   if (result[1] != 0) return;            // capacity exceeded: the layout kernel wrote nothing, neither do we
   const long long block = blockIdx.x;
   const int tid = threadIdx.x;
-  encode_phase_load(codes, block, tid, sh);
+  encode_phase_load(filt, n_total, codes, block, tid, sh);
   __syncthreads();
-  encode_phase_count(filt, n_total, block, tid, sh);
+  encode_phase_count(n_total, block, tid, sh);
   __syncthreads();
-  encode_phase_emit(filt, n_total, block, hdrs, meta, idat_off, out_words, tid, sh);
+  encode_phase_groups(tid, sh);
+  __syncthreads();
+  encode_phase_emit(n_total, block, hdrs, meta, idat_off, out_words, tid, sh);
 }
 
-__global__ void __launch_bounds__(kCrcThreads) png_crc_kernel(uint8_t* __restrict__ out, const long long* __restrict__ idat_off, long long nblocks,
-                                                             const long long* __restrict__ result) {
+__global__ void __launch_bounds__(kThreads) png_crc_kernel(uint8_t* __restrict__ out, const long long* __restrict__ idat_off,
+                                                          const long long* __restrict__ result) {
   __shared__ CrcShared sh;
   if (result[1] != 0) return;
-  crc_phase_table(threadIdx.x, sh);
+  const long long block = blockIdx.x;
+  const int tid = threadIdx.x;
+  crc_phase_tables(tid, sh);
   __syncthreads();
-  crc_phase_chunk(out, idat_off, nblocks, (long long)blockIdx.x * kCrcThreads + threadIdx.x, sh);
+  crc_phase_pieces(out, idat_off, block, tid, sh);
+  __syncthreads();
+  crc_phase_store(out, idat_off, block, tid, sh);
 }
 
 // workspace layout (32-bit words): adler_rows [2h] | codes [nb * kCodeStride] | hdrs [nb * kHdrWords] | meta [nb * 2] | pad | idat_off [nb + 1] (64-bit)
@@ -103,8 +113,8 @@ extern "C" int fd_png_encode(const uint8_t* image, int32_t h, int32_t w, int32_t
   FD_REQUIRE(image && filtered && work && out && result, "fd_png_encode: null pointer");
   FD_REQUIRE(h > 0 && w > 0 && channels >= 1 && channels <= 4, "fd_png_encode: bad shape %d x %d x %d", h, w, channels);
   FD_REQUIRE(row_stride_bytes >= (int64_t)w * channels, "fd_png_encode: row stride %lld < row bytes", (long long)row_stride_bytes);
-  FD_REQUIRE(((uintptr_t)out % 4) == 0 && ((uintptr_t)work % 8) == 0 && ((uintptr_t)result % 8) == 0 && out_capacity % 4 == 0,
-             "fd_png_encode: out must be 4-byte aligned with a capacity that is a multiple of 4, work / result 8-byte aligned");
+  FD_REQUIRE(((uintptr_t)out % 4) == 0 && ((uintptr_t)filtered % 4) == 0 && ((uintptr_t)work % 8) == 0 && ((uintptr_t)result % 8) == 0 && out_capacity % 4 == 0,
+             "fd_png_encode: out / filtered must be 4-byte aligned, the capacity a multiple of 4, work / result 8-byte aligned");
   const long long n_total = fd_png_filtered_bytes(h, w, channels);
   FD_REQUIRE(n_total < (1ll << 31), "fd_png_encode: image too large (%lld filtered bytes)", n_total);
   const long long nb = num_blocks(n_total);
@@ -122,8 +132,7 @@ extern "C" int fd_png_encode(const uint8_t* image, int32_t h, int32_t w, int32_t
                                       reinterpret_cast<long long*>(result));
   png_encode_kernel<<<(unsigned)nb, kThreads, 0, st>>>(filtered, n_total, codes, hdrs, meta, idat_off,
                                                        reinterpret_cast<const long long*>(result), reinterpret_cast<uint32_t*>(out));
-  png_crc_kernel<<<(unsigned)((nb + kCrcThreads - 1) / kCrcThreads), kCrcThreads, 0, st>>>(out, idat_off, nb,
-                                                                                          reinterpret_cast<const long long*>(result));
+  png_crc_kernel<<<(unsigned)nb, kThreads, 0, st>>>(out, idat_off, reinterpret_cast<const long long*>(result));
   g_launches += 5;
   FD_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -20,6 +20,7 @@
 // images comes from.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define FD_HD __host__ __device__ __forceinline__
@@ -37,16 +38,28 @@
 namespace fd {
 namespace png {
 
+// little-endian 32-bit load from a 4-byte aligned address
+FD_HD uint32_t load_u32(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  return *reinterpret_cast<const uint32_t*>(p);
+#else
+  uint32_t v;
+  memcpy(&v, p, 4);
+  return v;
+#endif
+}
+
 constexpr int kThreads = 256;                 // threads per block in every kernel below
 constexpr int kChunk = 16384;                 // filtered bytes per deflate block
 constexpr int kRun = kChunk / kThreads;       // consecutive bytes one thread encodes
+constexpr int kRunPadWords = kRun / 4 + 1;    // words between two runs of a block staged in shared memory (17: the 32 lanes of a
+                                              // warp, each walking its own run, start in 32 different banks)
 constexpr int kSyms = 286;                    // literals 0..255, end-of-block, length codes 257..285
 constexpr int kCodeStride = 288;              // words per block in the code table (286 padded)
 constexpr int kHdrWords = 72;                 // bit-packed block header, <= 17 + 57 + 287*7 = 2083 bits
 constexpr int kMinRun = 6;                    // equal bytes from which a run is coded as literal + match(distance 1)
 constexpr int kMaxLitBits = 15, kMaxClBits = 7;
 constexpr int kSigIhdrBytes = 8 + 25;         // signature + IHDR chunk
-constexpr int kCrcThreads = 64;               // threads per block of the CRC kernel (one IDAT chunk per thread)
 constexpr uint32_t kAdlerMod = 65521u;
 
 // per-block metadata written by the statistics kernel
@@ -154,6 +167,9 @@ struct CodeScratch {
   uint32_t count[32];            // symbols per code length
   uint32_t next_code[17];
   uint8_t len[288];              // code lengths of the alphabet being built
+  uint8_t lit_len[288];          // literal/length code lengths of the block
+  uint32_t lit_next[17];         // first canonical code of every literal/length code length
+  int dist_len;                  // 1 when the block has matches (one distance code of one bit), else 0
   uint8_t all_len[288];          // HLIT literal/length lengths + 1 distance length
   uint8_t tok_sym[288], tok_extra[288];
   uint32_t cl_freq[19];
@@ -161,10 +177,13 @@ struct CodeScratch {
   uint32_t cl_code[19];
 };
 
-FD_HD uint32_t reverse_bits(uint32_t v, int n) {
-  uint32_t r = 0;
-  for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1u); v >>= 1; }
-  return r;
+FD_HD uint32_t reverse_bits(uint32_t v, int n) {          // the low n bits of v in reverse order, 1 <= n <= 32
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  v = (v >> 16) | (v << 16);
+  return v >> (32 - n);
 }
 
 // Length-limited Huffman code lengths for freq[0..nsym): optimal tree (two-queue construction over radix-sorted
@@ -290,26 +309,45 @@ FD_HD int next_token(const uint8_t* p, int i, int m, int& match_len) {
   return 1;
 }
 
-// Builds the literal/length code of one deflate block from its token histogram (hist[0..286): literals, end-of-block
-// added here, length symbols), and the bit-packed dynamic-block header.  codes: kCodeStride words; hdr: kHdrWords words.
-FD_HD void build_block_code(const uint32_t* hist, CodeScratch& s, uint32_t* codes, uint32_t* hdr, BlockMeta* meta) {
-  uint32_t freq[kSyms];
+// The code of one deflate block from its token histogram hist[0..286) (literals, end-of-block, length symbols), in three
+// steps so that the per-symbol part runs on all threads:
+//   1 (one thread)   literal/length code lengths, first code of every length
+//   2 (every thread) canonical code of a symbol (RFC 1951 §3.2.2: codes of one length are consecutive in symbol order, so a
+//                    symbol's code is the first code of its length + the number of earlier symbols of that length) and the
+//                    bits its occurrences take
+//   3 (one thread)   the bit-packed dynamic-block header and the block's size
+FD_HD void build_lit_lengths(uint32_t* hist, CodeScratch& s) {
+  hist[256] = 1;                                           // one end-of-block per block
   uint32_t matches = 0;
-  for (int i = 0; i < kSyms; ++i) { freq[i] = hist[i]; if (i > 256) matches += hist[i]; }
-  freq[256] = 1;
-  huffman_lengths(freq, kSyms, kMaxLitBits, s);
-  canonical_codes(kSyms, kMaxLitBits, s, codes);
-  for (int i = kSyms; i < kCodeStride; ++i) codes[i] = 0;
-  // one distance code (distance 1), one bit long when the block has matches, absent (zero bits) when it is all literals
-  const int dist_len = matches ? 1 : 0;
-  unsigned long long data_bits = 0;
-  for (int i = 0; i < 256; ++i) data_bits += (unsigned long long)hist[i] * s.len[i];
-  for (int i = 257; i < kSyms; ++i) data_bits += (unsigned long long)hist[i] * (s.len[i] + length_extra_bits(i) + dist_len);
-  const int eob_len = s.len[256];
+  for (int i = 257; i < kSyms; ++i) matches += hist[i];
+  s.dist_len = matches ? 1 : 0;
+  huffman_lengths(hist, kSyms, kMaxLitBits, s);
+  for (int d = 0; d <= kMaxLitBits; ++d) s.count[d] = 0;
+  for (int i = 0; i < kSyms; ++i) { s.lit_len[i] = s.len[i]; ++s.count[s.len[i]]; }
+  s.count[0] = 0;
+  uint32_t code = 0;
+  s.lit_next[0] = 0;
+  for (int d = 1; d <= kMaxLitBits; ++d) { code = (code + s.count[d - 1]) << 1; s.lit_next[d] = code; }
+}
+// returns the bits all occurrences of `sym` take in the block (code + extra bits + distance code; end-of-block excluded)
+FD_HD unsigned long long build_lit_code(const uint32_t* hist, const CodeScratch& s, uint32_t* codes, int sym) {
+  if (sym >= kSyms) { codes[sym] = 0; return 0; }
+  const int l = s.lit_len[sym];
+  if (l == 0) { codes[sym] = 0; return 0; }
+  uint32_t rank = 0;
+  for (int j = 0; j < sym; ++j) rank += s.lit_len[j] == l;
+  codes[sym] = ((uint32_t)l << 16) | reverse_bits(s.lit_next[l] + rank, l);
+  if (sym < 256) return (unsigned long long)hist[sym] * l;
+  if (sym == 256) return 0;
+  return (unsigned long long)hist[sym] * (l + length_extra_bits(sym) + s.dist_len);
+}
+FD_HD void build_block_header(CodeScratch& s, unsigned long long data_bits, uint32_t* hdr, BlockMeta* meta) {
+  const int eob_len = s.lit_len[256];
   int hlit = kSyms;
-  while (hlit > 257 && s.len[hlit - 1] == 0) --hlit;
-  for (int i = 0; i < hlit; ++i) s.all_len[i] = s.len[i];
-  s.all_len[hlit] = (uint8_t)dist_len;
+  while (hlit > 257 && s.lit_len[hlit - 1] == 0) --hlit;
+  for (int i = 0; i < hlit; ++i) s.all_len[i] = s.lit_len[i];
+  // one distance code (distance 1), one bit long when the block has matches, absent (zero bits) when it is all literals
+  s.all_len[hlit] = (uint8_t)s.dist_len;
   // run-length tokens over the code lengths (§3.2.7: 16 = repeat previous 3-6, 17 = zeros 3-10, 18 = zeros 11-138)
   const int total_lens = hlit + 1;
   int ntok = 0;
@@ -358,23 +396,43 @@ FD_HD void build_block_code(const uint32_t* hist, CodeScratch& s, uint32_t* code
   meta->payload_bytes = (uint32_t)((bits_total + 7) / 8 + 4);
 }
 
+// ------------------------------------------------------------------------------------------------ a block in shared memory
+// The 16 KB of a block, copied with coalesced word loads; run r (the 64 bytes thread r tokenises) starts at word r * 17.
+struct StagedBlock {
+  uint32_t words[kThreads * kRunPadWords];
+};
+FD_HD void stage_phase_load(const uint8_t* filt, long long n_total, long long block, int tid, StagedBlock& st) {
+  const long long base = block * kChunk;
+  for (int wi = tid; wi < kChunk / 4; wi += kThreads) {
+    const long long off = base + 4ll * wi;
+    uint32_t v = 0;
+    if (off + 4 <= n_total) v = load_u32(filt + off);
+    else
+      for (int b = 0; b < 4; ++b)
+        if (off + b < n_total) v |= (uint32_t)filt[off + b] << (8 * b);
+    st.words[(wi / (kRun / 4)) * kRunPadWords + wi % (kRun / 4)] = v;
+  }
+}
+// thread tid's run: pointer into the staged block and its length (kRun, fewer or none at the end of the stream)
+FD_HD const uint8_t* staged_run(const StagedBlock& st, long long n_total, long long block, int tid, int& m) {
+  const long long left = n_total - (block * kChunk + (long long)tid * kRun);
+  m = left >= kRun ? kRun : (left > 0 ? (int)left : 0);
+  return reinterpret_cast<const uint8_t*>(st.words + tid * kRunPadWords);
+}
+
 struct StatsShared {
   uint32_t hist[288];
+  StagedBlock st;
   CodeScratch scratch;
+  unsigned long long part_bits[kThreads];
 };
-FD_HD void stats_phase_zero(int tid, StatsShared& sh) {
+FD_HD void stats_phase_stage(const uint8_t* filt, long long n_total, long long block, int tid, StatsShared& sh) {
   for (int i = tid; i < 288; i += kThreads) sh.hist[i] = 0;
+  stage_phase_load(filt, n_total, block, tid, sh.st);
 }
-// bytes of thread tid's run in `block` (kRun, fewer or none at the end of the stream)
-FD_HD int run_bytes(long long n_total, long long block, int tid, long long& begin) {
-  begin = block * kChunk + (long long)tid * kRun;
-  const long long left = n_total - begin;
-  return left >= kRun ? kRun : (left > 0 ? (int)left : 0);
-}
-FD_HD void stats_phase_hist(const uint8_t* filt, long long n_total, long long block, int tid, StatsShared& sh) {
-  long long begin;
-  const int m = run_bytes(n_total, block, tid, begin);
-  const uint8_t* p = filt + begin;
+FD_HD void stats_phase_hist(long long n_total, long long block, int tid, StatsShared& sh) {
+  int m;
+  const uint8_t* p = staged_run(sh.st, n_total, block, tid, m);
   for (int i = 0; i < m;) {
     int match_len;
     const int adv = next_token(p, i, m, match_len);
@@ -387,8 +445,20 @@ FD_HD void stats_phase_hist(const uint8_t* filt, long long n_total, long long bl
     i += adv;
   }
 }
-FD_HD void stats_phase_build(long long block, uint32_t* codes, uint32_t* hdrs, BlockMeta* meta, int tid, StatsShared& sh) {
-  if (tid == 0) build_block_code(sh.hist, sh.scratch, codes + block * kCodeStride, hdrs + block * kHdrWords, meta + block);
+FD_HD void stats_phase_lengths(int tid, StatsShared& sh) {
+  if (tid == 0) build_lit_lengths(sh.hist, sh.scratch);
+}
+FD_HD void stats_phase_codes(long long block, uint32_t* codes, int tid, StatsShared& sh) {
+  unsigned long long bits = build_lit_code(sh.hist, sh.scratch, codes + block * kCodeStride, tid);
+  if (tid + kThreads < kCodeStride) bits += build_lit_code(sh.hist, sh.scratch, codes + block * kCodeStride, tid + kThreads);
+  sh.part_bits[tid] = bits;
+}
+FD_HD void stats_phase_header(long long block, uint32_t* hdrs, BlockMeta* meta, int tid, StatsShared& sh) {
+  if (tid == 0) {
+    unsigned long long data_bits = 0;
+    for (int k = 0; k < kThreads; ++k) data_bits += sh.part_bits[k];
+    build_block_header(sh.scratch, data_bits, hdrs + block * kHdrWords, meta + block);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ CRC-32 / Adler-32
@@ -520,18 +590,21 @@ FD_HD void bw_flush(BitWriter& w) {
   w.acc = 0; w.nbits = 0;
 }
 
+constexpr int kScanGroup = 16;                 // threads per group of the two-level scan of the bit counts
 struct EncodeShared {
   uint32_t codes[kCodeStride];
   uint32_t cnt[kThreads];
+  uint32_t group[kThreads / kScanGroup];
+  StagedBlock st;
 };
-FD_HD void encode_phase_load(const uint32_t* codes, long long block, int tid, EncodeShared& sh) {
+FD_HD void encode_phase_load(const uint8_t* filt, long long n_total, const uint32_t* codes, long long block, int tid, EncodeShared& sh) {
   for (int i = tid; i < kCodeStride; i += kThreads) sh.codes[i] = codes[block * kCodeStride + i];
+  stage_phase_load(filt, n_total, block, tid, sh.st);
 }
 // bits of the tokens of this thread's run
-FD_HD void encode_phase_count(const uint8_t* filt, long long n_total, long long block, int tid, EncodeShared& sh) {
-  long long begin;
-  const int m = run_bytes(n_total, block, tid, begin);
-  const uint8_t* p = filt + begin;
+FD_HD void encode_phase_count(long long n_total, long long block, int tid, EncodeShared& sh) {
+  int m;
+  const uint8_t* p = staged_run(sh.st, n_total, block, tid, m);
   uint32_t bits = 0;
   for (int i = 0; i < m;) {
     int match_len;
@@ -546,13 +619,22 @@ FD_HD void encode_phase_count(const uint8_t* filt, long long n_total, long long 
   }
   sh.cnt[tid] = bits;
 }
+// totals of groups of 16 threads (first level of the scan)
+FD_HD void encode_phase_groups(int tid, EncodeShared& sh) {
+  if (tid < kThreads / kScanGroup) {
+    uint32_t t = 0;
+    for (int k = 0; k < kScanGroup; ++k) t += sh.cnt[tid * kScanGroup + k];
+    sh.group[tid] = t;
+  }
+}
 // thread 0 also writes the block header, the last thread the end-of-block code and the byte-aligning stored block
-FD_HD void encode_phase_emit(const uint8_t* filt, long long n_total, long long block, const uint32_t* hdrs, const BlockMeta* meta,
+FD_HD void encode_phase_emit(long long n_total, long long block, const uint32_t* hdrs, const BlockMeta* meta,
                              const long long* idat_off, uint32_t* out_words, int tid, EncodeShared& sh) {
   const unsigned long long base_bit = 8ull * (unsigned long long)block_payload_offset(idat_off, block);
   const uint32_t hdr_bits = meta[block].hdr_bits;
   unsigned long long before = 0;
-  for (int k = 0; k < tid; ++k) before += sh.cnt[k];
+  for (int g = 0; g < tid / kScanGroup; ++g) before += sh.group[g];
+  for (int k = (tid / kScanGroup) * kScanGroup; k < tid; ++k) before += sh.cnt[k];
   BitWriter bw;
   if (tid == 0) {
     bw_init(bw, out_words, base_bit);
@@ -566,9 +648,8 @@ FD_HD void encode_phase_emit(const uint8_t* filt, long long n_total, long long b
     bw_flush(bw);
   }
   bw_init(bw, out_words, base_bit + hdr_bits + before);
-  long long begin;
-  const int m = run_bytes(n_total, block, tid, begin);
-  const uint8_t* p = filt + begin;
+  int m;
+  const uint8_t* p = staged_run(sh.st, n_total, block, tid, m);
   for (int i = 0; i < m;) {
     int match_len;
     const int adv = next_token(p, i, m, match_len);
@@ -596,20 +677,60 @@ FD_HD void encode_phase_emit(const uint8_t* filt, long long n_total, long long b
 }
 
 // ------------------------------------------------------------------------------------------------ IDAT CRCs
+// One CTA per IDAT chunk.  CRC-32 is linear over GF(2): for a message cut into pieces m_0 .. m_k,
+//   crc(m_0 .. m_k) = XOR_i  x^(8 * bytes after piece i) * crc(m_i)   (mod P; the identity zlib's crc32_combine uses),
+// so every thread takes the CRC of its own piece with the byte table, multiplies it by the power of x that stands for the
+// bytes behind it (square-and-multiply over x^(8 * 2^k), 32-step carry-less multiplications), and one thread XORs the parts.
+// Polynomials in the reflected representation of the CRC register: bit 31 = x^0, bit 0 = x^31.
+FD_HD uint32_t gf2_mulmod(uint32_t a, uint32_t b) {
+  uint32_t p = 0;
+  for (int i = 0; i < 32; ++i) {
+    if (a & (0x80000000u >> i)) p ^= b;
+    b = (b & 1u) ? (b >> 1) ^ 0xedb88320u : b >> 1;       // b *= x
+  }
+  return p;
+}
+constexpr int kCrcPowers = 20;                 // an IDAT chunk (at most 9/8 of 16 KB + header) is far below 2^20 bytes
 struct CrcShared {
   uint32_t table[256];
+  uint32_t pow8[kCrcPowers];     // x^(8 * 2^k) mod P
+  uint32_t part[kThreads];
 };
-FD_HD void crc_phase_table(int tid, CrcShared& sh) {
-  for (int i = tid; i < 256; i += kCrcThreads) sh.table[i] = crc_table_entry((uint32_t)i);
+FD_HD void crc_phase_tables(int tid, CrcShared& sh) {
+  for (int i = tid; i < 256; i += kThreads) sh.table[i] = crc_table_entry((uint32_t)i);
+  if (tid < kCrcPowers) {
+    uint32_t v = 0x40000000u;                              // x^1
+    for (int k = 0; k < tid + 3; ++k) v = gf2_mulmod(v, v);
+    sh.pow8[tid] = v;
+  }
 }
-// one IDAT chunk per thread: CRC over the chunk type + payload, stored big-endian behind the payload
-FD_HD void crc_phase_chunk(uint8_t* out, const long long* idat_off, long long nblocks, long long block, const CrcShared& sh) {
-  if (block >= nblocks) return;
+// CRC range of a chunk: its type + payload, n bytes from out + idat_off[block] + 4
+FD_HD void crc_phase_pieces(const uint8_t* out, const long long* idat_off, long long block, int tid, CrcShared& sh) {
   const uint8_t* p = out + idat_off[block] + 4;
   const long long n = idat_off[block + 1] - idat_off[block] - 8;
-  uint32_t crc = 0xffffffffu;
-  for (long long i = 0; i < n; ++i) crc = sh.table[(crc ^ p[i]) & 255u] ^ (crc >> 8);
-  put_be32(out + idat_off[block + 1] - 4, ~crc);
+  const long long piece = (n + kThreads - 1) / kThreads;
+  const long long begin = tid * piece;
+  long long end = begin + piece;
+  if (end > n) end = n;
+  uint32_t part = 0;
+  if (begin < end) {
+    uint32_t crc = 0xffffffffu;
+    for (long long i = begin; i < end; ++i) crc = sh.table[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+    crc = ~crc;
+    unsigned long long behind = (unsigned long long)(n - end);
+    uint32_t shift = 0x80000000u;                          // x^0
+    for (int k = 0; behind; ++k, behind >>= 1)
+      if (behind & 1) shift = gf2_mulmod(shift, sh.pow8[k]);
+    part = gf2_mulmod(shift, crc);
+  }
+  sh.part[tid] = part;
+}
+FD_HD void crc_phase_store(uint8_t* out, const long long* idat_off, long long block, int tid, const CrcShared& sh) {
+  if (tid == 0) {
+    uint32_t crc = 0;
+    for (int k = 0; k < kThreads; ++k) crc ^= sh.part[k];
+    put_be32(out + idat_off[block + 1] - 4, crc);
+  }
 }
 
 FD_HD long long num_blocks(long long n_total) { return (n_total + kChunk - 1) / kChunk; }

@@ -36,21 +36,34 @@ def _as_device_u8(image, device):
     return t
 
 
-def encode_png(image, device="cuda"):
-    """PNG file (bytes) of `image`: u8 HWC / HW CUDA tensor (rows may be a strided view), or a PIL image / numpy array / host
-    tensor that is uploaded first."""
+_pinned = {}
+
+
+def _encode_to_pinned(image, device):
+    """Runs the encoder and returns the file as a numpy view of a cached pinned host buffer (valid until the next call)."""
     t = _as_device_u8(image, device)
     with torch.cuda.device(t.device):
         out, result = ops.png_encode(t)
-        size, overflow = result.tolist()                               # the one synchronisation
+        size, overflow = result.tolist()                               # first synchronisation: 16 bytes
         if overflow:
             raise RuntimeError("encode_png: output capacity exceeded (%d bytes needed)" % size)
-        return out[:size].cpu().numpy().tobytes()
+        host = _pinned.get("buf")
+        if host is None or host.numel() < size:
+            host = _pinned["buf"] = torch.empty(max(size, out.numel()), dtype=torch.uint8, pin_memory=True)
+        host[:size].copy_(out[:size], non_blocking=True)               # only the finished file crosses PCIe, into pinned memory
+        torch.cuda.current_stream().synchronize()
+        return host.numpy()[:size]
+
+
+def encode_png(image, device="cuda"):
+    """PNG file (bytes) of `image`: u8 HWC / HW CUDA tensor (rows may be a strided view), or a PIL image / numpy array / host
+    tensor that is uploaded first."""
+    return _encode_to_pinned(image, device).tobytes()
 
 
 def save_png(image, fp, device="cuda"):
     """`image.save(fp)` for PNG: fp is a path or a binary file object."""
-    data = encode_png(image, device)
+    data = memoryview(_encode_to_pinned(image, device))
     if hasattr(fp, "write"):
         fp.write(data)
     else:

@@ -41,6 +41,14 @@ try:
         data = fd.encode_png(img)
     res["encode_png_ms_incl_d2h_of_the_file"] = (time.perf_counter() - t0) / 5 * 1e3
     res["file_bytes"] = len(data)
+    tmp = "/dev/shm/fd_png_check.png" if os.path.isdir("/dev/shm") else os.path.join(OUT, "fd_png_check.png")
+    fd.save_png(img, tmp)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        fd.save_png(img, tmp)
+    res["save_png_ms_to_tmpfs"] = (time.perf_counter() - t0) / 5 * 1e3
+    res["saved_file_equals_encode_png"] = open(tmp, "rb").read() == data
+    os.remove(tmp)
     host = img.cpu().numpy()
     pil = Image.fromarray(host)
     t0 = time.perf_counter(); buf = io.BytesIO(); pil.save(buf, format="PNG"); res["pil_save_ms"] = (time.perf_counter() - t0) * 1e3

@@ -42,9 +42,11 @@ extern "C" int emul_png_encode(const unsigned char* image, int h, int w, int cha
   {
     StatsShared* sh = new StatsShared;
     for (long long b = 0; b < nb; ++b) {
-      for (int t = 0; t < kThreads; ++t) stats_phase_zero(t, *sh);
-      for (int t = 0; t < kThreads; ++t) stats_phase_hist(filt.data(), n_total, b, t, *sh);
-      for (int t = 0; t < kThreads; ++t) stats_phase_build(b, codes.data(), hdrs.data(), meta.data(), t, *sh);
+      for (int t = 0; t < kThreads; ++t) stats_phase_stage(filt.data(), n_total, b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) stats_phase_hist(n_total, b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) stats_phase_lengths(t, *sh);
+      for (int t = 0; t < kThreads; ++t) stats_phase_codes(b, codes.data(), t, *sh);
+      for (int t = 0; t < kThreads; ++t) stats_phase_header(b, hdrs.data(), meta.data(), t, *sh);
     }
     delete sh;
   }
@@ -60,20 +62,22 @@ extern "C" int emul_png_encode(const unsigned char* image, int h, int w, int cha
   {
     EncodeShared* sh = new EncodeShared;
     for (long long b = 0; b < nb; ++b) {
-      for (int t = 0; t < kThreads; ++t) encode_phase_load(codes.data(), b, t, *sh);
-      for (int t = 0; t < kThreads; ++t) encode_phase_count(filt.data(), n_total, b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) encode_phase_load(filt.data(), n_total, codes.data(), b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) encode_phase_count(n_total, b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) encode_phase_groups(t, *sh);
       for (int t = 0; t < kThreads; ++t)
-        encode_phase_emit(filt.data(), n_total, b, hdrs.data(), meta.data(), idat_off.data(), reinterpret_cast<uint32_t*>(out), t, *sh);
+        encode_phase_emit(n_total, b, hdrs.data(), meta.data(), idat_off.data(), reinterpret_cast<uint32_t*>(out), t, *sh);
     }
     delete sh;
   }
   {
-    CrcShared sh;
-    const long long grid = (nb + kCrcThreads - 1) / kCrcThreads;
-    for (long long g = 0; g < grid; ++g) {
-      for (int t = 0; t < kCrcThreads; ++t) crc_phase_table(t, sh);
-      for (int t = 0; t < kCrcThreads; ++t) crc_phase_chunk(out, idat_off.data(), nb, g * kCrcThreads + t, sh);
+    CrcShared* sh = new CrcShared;
+    for (long long b = 0; b < nb; ++b) {
+      for (int t = 0; t < kThreads; ++t) crc_phase_tables(t, *sh);
+      for (int t = 0; t < kThreads; ++t) crc_phase_pieces(out, idat_off.data(), b, t, *sh);
+      for (int t = 0; t < kThreads; ++t) crc_phase_store(out, idat_off.data(), b, t, *sh);
     }
+    delete sh;
   }
   if (filtered_out) memcpy(filtered_out, filt.data(), n_total);
   return 0;
