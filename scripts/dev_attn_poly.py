@@ -1,12 +1,11 @@
 """Dev (GPU): fd_attention_d64 correctness (vs torch SDPA in fp32) and TFLOP/s at the tile-step's two self-attention shapes,
-for the variant selected by FD_ATTN_POLY (0 = all exponentials on MUFU; 2/3/4 of every 8 pairs on the FMA pipe) and
-FD_ATTN_W8 (1 = eight softmax warps, two threads per query row)."""
+for the variant selected by FD_ATTN_POLY (0 = all exponentials on MUFU; 2/3/4 of every 8 pairs on the FMA pipe)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
 from faithdiff_dev_b200 import ops
-tag = "FD_ATTN_POLY=%s FD_ATTN_W8=%s" % (os.environ.get("FD_ATTN_POLY", "0"), os.environ.get("FD_ATTN_W8", "0"))
+tag = "FD_ATTN_POLY=%s" % os.environ.get("FD_ATTN_POLY", "0")
 torch.manual_seed(0)
 for B, H, L, spread in [(2, 3, 640, 1.0), (1, 2, 1000, 6.0), (1, 1, 130, 1.0), (2, 2, 200, 30.0), (14, 10, 4096, 1.0), (14, 20, 1024, 1.0)]:
     qkv = (torch.randn(B * L, 3 * H * 64, device="cuda") * spread).to(torch.bfloat16)

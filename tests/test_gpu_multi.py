@@ -26,7 +26,8 @@ def test_two_rank_pipeline_matches_single_rank():
 @pytest.mark.skipif(os.environ.get("FD_TEST_EXPERIMENTAL") != "1", reason="opt-in path; set FD_TEST_EXPERIMENTAL=1")
 def test_two_rank_pipeline_with_peer_memory_exchange():
     """Same check with FD_P2P_EXCHANGE=1: the per-step exchange as one kernel over NVLink peer memory (dist.PeerCanvas,
-    csrc/peer_exchange.cu) instead of the NCCL all-reduce.  EXPERIMENTAL: not yet run on a multi-GPU box; run under `timeout`."""
+    csrc/peer_exchange.cu) instead of the NCCL all-reduce.  Opt-in like the path itself (measured on 2 and 8 GPUs in round 2:
+    correct, not faster than NCCL — DESIGN §6), so the default suite does not depend on peer access between the box's GPUs."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
