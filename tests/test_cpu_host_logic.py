@@ -27,6 +27,19 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert m and ctypes.sizeof(_lib.GemmDesc) == lib.fd_sizeof_gemm_desc() == 176
 
 
+def test_cabi_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ types, no torch types) and as C++."""
+    import shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "faithdiff_b200.h"\nint main(void) { return fd_version == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-pedantic", "-Werror", "-fsyntax-only"], ["g++", "-std=c++17", "-Werror", "-fsyntax-only", "-x", "c++"]):
+        r = subprocess.run(cmd + ["-I", inc, str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
 def test_no_cuda_no_fallback():
     """The product path must fail loudly without a GPU — never compute on the CPU."""
     import faithdiff_dev_b200 as fd
