@@ -92,8 +92,8 @@ def exchange_canvas(numerator, group=None):
 
 
 class PeerCanvas:
-    """Opt-in (FD_P2P_EXCHANGE=1; not yet run on a multi-GPU box): the per-step exchange as ONE kernel over NVLink peer memory
-    instead of an NCCL all-reduce + fd_canvas_finalize (csrc/peer_exchange.cu).  Every rank's fp32 numerator canvas lives in a
+    """Opt-in (FD_P2P_EXCHANGE=1; run on 2 and 8 B200s in round 2: correct, not faster than NCCL — DESIGN §6): the per-step
+    exchange as ONE kernel over NVLink peer memory instead of an NCCL all-reduce + fd_canvas_finalize (csrc/peer_exchange.cu).  Every rank's fp32 numerator canvas lives in a
     cudaMalloc'd region that all ranks of the node map through CUDA IPC; `numerator(step)` is the slot this rank accumulates
     step `step` into, `exchange_finalize(step, count, dtype)` publishes it, waits for the peers, sums all canvases in rank
     order and divides by the count map.  torch.distributed only carries the 64-byte IPC handles, once."""
