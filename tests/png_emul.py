@@ -37,13 +37,16 @@ def load():
         lib.emul_png_encode.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_longlong,
                                         C.POINTER(C.c_longlong), C.c_void_p]
         lib.emul_huffman_lengths.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        lib.emul_set_thread_order.argtypes = [C.c_int, C.c_uint]
         _lib = lib
     return _lib
 
 
-def encode(a, capacity=None):
-    """a: u8 HW / HWC numpy array (any row stride) -> (png file bytes, filtered scanline stream)."""
+def encode(a, capacity=None, thread_order=0, seed=1):
+    """a: u8 HW / HWC numpy array (any row stride) -> (png file bytes, filtered scanline stream).
+    thread_order: order of a block's threads inside each phase (0 ascending, 1 descending, 2 shuffled per phase)."""
     lib = load()
+    lib.emul_set_thread_order(thread_order, seed)
     if a.ndim == 2:
         a = a[..., None]
     assert a.dtype == np.uint8 and a.strides[2] == 1 and a.strides[1] == a.shape[2]

@@ -76,6 +76,17 @@ def test_emulated_encoder_decodes_with_pil_and_zlib(name):
     assert (back.reshape(a3.shape) == a3).all()
 
 
+@pytest.mark.parametrize("name", ["mixed", "runs", "noise", "crop_view", "block_plus_one"])
+def test_file_does_not_depend_on_thread_order(name):
+    """Within a phase the device runs a block's threads in any order; the emulation must give the same bytes ascending,
+    descending and shuffled (a difference = two threads of one phase sharing a word, i.e. a missing barrier)."""
+    a = IMAGES[name]
+    want = png_emul.encode(a)[0]
+    assert png_emul.encode(a, thread_order=1)[0] == want
+    for seed in (1, 2, 3):
+        assert png_emul.encode(a, thread_order=2, seed=seed)[0] == want
+
+
 def test_compression_is_in_pil_range():
     """Not a parity quantity (two encoders never produce the same file) — a sanity band against PIL's default encoder."""
     for name, lo, hi in (("smooth_rgb", 0.0, 1.05), ("rgba", 0.0, 1.05), ("noise", 0.0, 1.05), ("mixed", 0.0, 1.15)):
