@@ -22,10 +22,15 @@
 #include <stdint.h>
 #include <string.h>
 
+// In the product (nvcc) the phase functions exist as DEVICE code only — the library has no host version of the encoder and
+// no CPU fallback; under g++ (the test harness) the same text is plain inline C++.  FD_HOST_HD marks the two size formulas the
+// host side of the C-ABI needs as well.
 #if defined(__CUDACC__)
-#define FD_HD __host__ __device__ __forceinline__
+#define FD_HD __device__ __forceinline__
+#define FD_HOST_HD __host__ __device__ __forceinline__
 #else
 #define FD_HD inline
+#define FD_HOST_HD inline
 #endif
 #if defined(__CUDA_ARCH__)
 #define FD_PNG_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -733,9 +738,9 @@ FD_HD void crc_phase_store(uint8_t* out, const long long* idat_off, long long bl
   }
 }
 
-FD_HD long long num_blocks(long long n_total) { return (n_total + kChunk - 1) / kChunk; }
+FD_HOST_HD long long num_blocks(long long n_total) { return (n_total + kChunk - 1) / kChunk; }
 // generous bound on the file size: a block's literals cost at most 9 bits per byte under its own optimal code
-FD_HD long long file_capacity(long long n_total) {
+FD_HOST_HD long long file_capacity(long long n_total) {
   return kSigIhdrBytes + 12 + n_total + n_total / 8 + num_blocks(n_total) * (12 + kHdrWords * 4 + 16) + 64;
 }
 
