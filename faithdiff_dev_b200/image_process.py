@@ -18,6 +18,19 @@ _PRECISION_BITS = 32 - 8 - 2          # Pillow: 8-bit samples, 2 guard bits for 
 
 
 def check_image_size(x, padder_size=8):
+    """utils/image_process.py:7-35.  x: PIL image (as in the reference) or a u8 HWC tensor (e.g. the device result of
+    `resize_lanczos`, which then never leaves the GPU); returns (padded image of the same kind, w0, h0, w, h)."""
+    if not hasattr(x, "size") or callable(getattr(x, "size")):       # torch tensor: .size is a method, PIL: a (w, h) tuple
+        import torch
+        assert x.dim() == 3 and x.dtype == torch.uint8, "u8 HWC tensor expected"
+        height, width = x.shape[0], x.shape[1]
+        mod_pad_h = (padder_size - height % padder_size) % padder_size
+        mod_pad_w = (padder_size - width % padder_size) % padder_size
+        if mod_pad_w:
+            x = torch.cat([x, x[:, -1:].expand(-1, mod_pad_w, -1)], dim=1)
+        if mod_pad_h:
+            x = torch.cat([x, x[-1:].expand(mod_pad_h, -1, -1)], dim=0)
+        return x, width, height, width + mod_pad_w, height + mod_pad_h
     width, height = x.size
     mod_pad_h = (padder_size - height % padder_size) % padder_size
     mod_pad_w = (padder_size - width % padder_size) % padder_size

@@ -168,6 +168,9 @@ def test_check_image_size_matches_oracle():
         a, b = check_image_size(img), O.check_image_size(img)
         assert a[1:] == b[1:] and np.array_equal(np.asarray(a[0]), np.asarray(b[0]))
         assert a[3] % 8 == 0 and a[4] % 8 == 0
+        # the tensor form (what `resize_lanczos` returns, padded without leaving the device) is the same operation
+        t = check_image_size(torch.from_numpy(np.asarray(img).copy()))
+        assert t[1:] == b[1:] and np.array_equal(t[0].numpy(), np.asarray(b[0]))
 
 
 def test_quantize_8bit_state_dict():
