@@ -7,6 +7,7 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/val_tests.log 2>&1; e
 tail -n 4 gpurun_out/val_tests.log | cut -c1-300
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/val_smoke.log 2>&1; echo "smoke rc=$?"; tail -n 3 gpurun_out/val_smoke.log
 timeout 300 python scripts/dev_callers_bench.py > gpurun_out/val_callers.log 2>&1; echo "callers rc=$?"; tail -n 4 gpurun_out/val_callers.log
+timeout 200 python scripts/gpu_png_check.py > gpurun_out/val_png.log 2>&1; echo "png rc=$?"; tail -n 3 gpurun_out/val_png.log | cut -c1-600
 timeout 900 python bench.py > gpurun_out/val_bench.json 2> gpurun_out/val_bench.err; echo "bench rc=$?"
 cut -c1-3500 gpurun_out/val_bench.json
 timeout 300 python scripts/dev_norm_bench.py gns > gpurun_out/val_norm_bench.log 2>&1; tail -n 8 gpurun_out/val_norm_bench.log
