@@ -87,6 +87,34 @@ def test_file_does_not_depend_on_thread_order(name):
         assert png_emul.encode(a, thread_order=2, seed=seed)[0] == want
 
 
+def test_round_trip_property():
+    """Property over random shapes and contents (hypothesis): decode(encode(x)) == x through PIL, whatever the shape, the
+    channel count, the row stride or the statistics (noise, few levels, long runs)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=80, deadline=None, derandomize=True)
+    @given(st.integers(1, 40), st.integers(1, 900), st.integers(1, 4), st.integers(0, 3), st.integers(0, 2 ** 31 - 1), st.integers(0, 5))
+    def prop(h, w, c, kind, seed, crop):
+        rng = np.random.default_rng(seed)
+        full = (h + crop, w + crop, c)
+        if kind == 0:
+            a = rng.integers(0, 256, full, dtype=np.uint8)
+        elif kind == 1:
+            a = (rng.integers(0, 3, full) * 127).astype(np.uint8)
+        elif kind == 2:
+            k = int(rng.integers(1, 80))
+            a = np.repeat(rng.integers(0, 256, (full[0], (full[1] + k - 1) // k, c), dtype=np.uint8), k, axis=1)[:, :full[1]]
+        else:
+            a = np.full(full, int(rng.integers(0, 256)), np.uint8)
+        a = np.ascontiguousarray(a)[crop:, crop:] if crop else np.ascontiguousarray(a)     # crop > 0: strided rows
+        data, _ = png_emul.encode(a)
+        im = Image.open(io.BytesIO(data))
+        im.load()
+        assert (np.asarray(im).reshape(a.shape) == a).all()
+
+    prop()
+
+
 def test_compression_is_in_pil_range():
     """Not a parity quantity (two encoders never produce the same file) — a sanity band against PIL's default encoder."""
     for name, lo, hi in (("smooth_rgb", 0.0, 1.05), ("rgba", 0.0, 1.05), ("noise", 0.0, 1.05), ("mixed", 0.0, 1.15)):
