@@ -8,6 +8,8 @@ file differs from PIL's (other filter / deflate choices), as two encoders' files
 PNG *decode* of the LQ input stays on the host (`Image.open`): an inflate stream is one serial dependency chain, the LQ image
 is a quarter of the output, and its decode overlaps the previous image's restoration.
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -37,6 +39,7 @@ def _as_device_u8(image, device):
 
 
 _pinned = {}
+_pinned_lock = threading.Lock()          # the staging buffer is shared: one encode at a time per process
 
 
 def _encode_to_pinned(image, device):
@@ -58,14 +61,16 @@ def _encode_to_pinned(image, device):
 def encode_png(image, device="cuda"):
     """PNG file (bytes) of `image`: u8 HWC / HW CUDA tensor (rows may be a strided view), or a PIL image / numpy array / host
     tensor that is uploaded first."""
-    return _encode_to_pinned(image, device).tobytes()
+    with _pinned_lock:
+        return _encode_to_pinned(image, device).tobytes()
 
 
 def save_png(image, fp, device="cuda"):
     """`image.save(fp)` for PNG: fp is a path or a binary file object."""
-    data = memoryview(_encode_to_pinned(image, device))
-    if hasattr(fp, "write"):
-        fp.write(data)
-    else:
-        with open(fp, "wb") as f:
-            f.write(data)
+    with _pinned_lock:
+        data = memoryview(_encode_to_pinned(image, device))
+        if hasattr(fp, "write"):
+            fp.write(data)
+        else:
+            with open(fp, "wb") as f:
+                f.write(data)
